@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the segment + CC hot path (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path (net forward, logit threshold, connected components, boxes) over
+one batch of synthetic 1024x1024 grayscale images per GPU (BASELINE configs[1]: batch 64).
+  value     inputs resident in HBM, device-timed with CUDA events on the launching stream,
+            max over ranks, whole-job images/sec
+  e2e       same metric through the reference-facing C-ABI call (ubd_segment) with pinned HOST
+            buffers: H2D of the images and D2H of mask + components inside the timed region
+  roofline  the dominant kernel (dilated 3x3 conv) vs the measured bf16 tensor peak (tf32 = 1/2)
+  cpu_baseline  the CPU oracle (torch-CPU restatement of the reference + its cv2 calls) on a bounded
+            sample, rank 0, N=1 only
+`--impl reference` times that CPU restatement as the reference arm (TF/Keras cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec at 1024x1024 (net+CC postproc)"
+ALGO_MAC_PER_INPUT_PX = 2201.25          # whole forward, C = 0
+DIL_MAC_PER_MAP_PX = 5184                # one dilated 3x3 24->24 layer
+ALGO_BYTES_PER_IMAGE_1024 = 4784128      # SURVEY.md 8d (f32 in + logits + mask + labels)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nme, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_images(batch, size, seed=1):
+    """`batch` uint8 images of size x size: 8 distinct synthetic images, tiled (synthetic data)."""
+    from ubdvss_b200 import synth
+    base = synth.synth_images(min(batch, 8), size, size, seed=seed)
+    reps = -(-batch // base.shape[0])
+    return np.ascontiguousarray(np.concatenate([base] * reps, 0)[:batch])
+
+
+def cpu_reference_step(weights, images_u8, thr):
+    """One pass of the CPU restatement of the reference over `images_u8` (oracle, test infra)."""
+    from oracle import net as onet, postproc as pp
+    x = onet.preprocess(images_u8.astype(np.float64), "mobilenet_like").astype(np.float32)
+    logits = onet.forward_torch(weights, x)
+    det = pp.threshold_mask(logits[..., :1], thr)
+    return [pp.postprocess_cv2(det[i], None, 4, 5) for i in range(det.shape[0])]
+
+
+def time_cpu(weights, images_u8, thr, steps, warmup):
+    import torch
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    for _ in range(warmup):
+        cpu_reference_step(weights, images_u8, thr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(weights, images_u8, thr)
+    dt = time.perf_counter() - t0
+    return images_u8.shape[0] * steps / dt, dt / steps, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE configs[1])")
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from oracle import net as onet, postproc as pp      # oracle: weights init + CPU baseline only
+
+    weights = onet.init_weights(0, seed=1234)
+    cfg = {"workload": f"configs[1]: batch-{args.batch} synthetic {args.size}x{args.size} grayscale inference per GPU, "
+                       f"{args.precision}, threshold + CC boxes", "batch_per_gpu": args.batch, "image": [args.size, args.size, 1],
+           "input_dtype": "uint8 (mobilenet_like preprocessing folded into L1)", "precision": args.precision,
+           "parallelism": f"batch-sharded x{world}, no collective",
+           "l2": "inputs larger than L2 (batch is 64 MiB uint8 + 100 MiB of maps per chunk sweep)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        imgs = make_images(args.cpu_sample, args.size)
+        xs = onet.preprocess(imgs[:1].astype(np.float64), "mobilenet_like").astype(np.float32)
+        thr = float(np.quantile(onet.forward_torch(weights, xs)[..., 0], 0.9))
+        v, step_s, cores = time_cpu(weights, imgs, thr, max(1, args.steps), max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
+                                 "sample": f"{args.cpu_sample} images of {args.size}x{args.size} per step (torch-CPU "
+                                           "restatement of net.py + the reference's cv2 post-processing; TF/Keras absent)"},
+                "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    from ubdvss_b200 import _lib
+    from ubdvss_b200.engine import Engine
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    eng = Engine(device=local_rank, precision=args.precision)
+    eng.set_weights(weights)
+    B, S = args.batch, args.size
+    imgs = make_images(B, S, seed=1 + rank)
+    pinned = torch.from_numpy(imgs).pin_memory()
+    h_imgs = pinned.numpy()
+    d_imgs = pinned.cuda(non_blocking=False)
+    d_mask = torch.empty((B, S // 4, S // 4), dtype=torch.uint8, device="cuda")
+    d_logits = torch.empty((B, S // 4, S // 4, 1), dtype=torch.float32, device="cuda")
+    # threshold at the 0.9 quantile of this model's logits so ~10 % of the map is positive
+    thr = float(np.quantile(eng.forward(imgs[:2], _lib.PREPROC_MOBILENET)[..., 0], 0.9))
+    min_area_x2 = 10
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    def step_dev():
+        return eng.segment_dev(d_imgs.data_ptr(), _lib.UBD_U8, B, S, S, thr, min_area_x2, _lib.PREPROC_MOBILENET,
+                               d_mask.data_ptr(), d_logits.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        comps, counts = step_dev()
+    eng.set_option("profile", 1)
+    barrier()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            comps, counts = step_dev()
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    dil_ms, dil_n = eng.stat("dilconv_ms"), eng.stat("dilconv_launches")
+    stem_ms, ccl_ms, head_ms = eng.stat("stem_ms"), eng.stat("ccl_ms"), eng.stat("head_ms")
+    eng.set_option("profile", 0)
+
+    # end to end through the host-buffer ABI call (what ModelRunner.predict does)
+    mask_h = torch.empty((B, S // 4, S // 4), dtype=torch.uint8).pin_memory().numpy()
+    def step_e2e():
+        x = h_imgs
+        n = x.shape[0]
+        cap = 64 * n
+        comps_h = np.zeros(cap, _lib.COMPONENT_DTYPE)
+        counts_h = np.zeros(n, np.int32)
+        _lib.check(eng.handle, eng._lib.ubd_segment(eng.handle, _lib.ptr(x), _lib.UBD_U8, n, S, S, _lib.PREPROC_MOBILENET,
+                                                     np.float32(thr), min_area_x2, _lib.ptr(mask_h), None, None,
+                                                     _lib.ptr(comps_h), cap, _lib.ptr(counts_h)))
+        return counts_h
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        counts_h = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    n_comp_last = int(counts_h.sum())
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_images = B * world * args.steps
+    value = total_images / (ms_max / 1e3)
+    e2e_value = total_images / (e2e_ms_max / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        q_px = (S // 4) * (S // 4)
+        # dominant kernel = the dilated conv; one launch processes one chunk of images through one layer
+        imgs_per_launch = B * 6 * args.steps / max(dil_n, 1)
+        flops_per_launch = 2.0 * DIL_MAC_PER_MAP_PX * q_px * imgs_per_launch
+        avg_launch_s = dil_ms / 1e3 / max(dil_n, 1)
+        achieved_tf = flops_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
+        peak_tf = pk["bf16_tflops_sustained"] * (0.5 if args.precision in ("fp32", "tf32") else 1.0)
+        roof = {"bound": "tensor", "kernel": "dilated 3x3 conv 24->24 (L4-L9)", "achieved": achieved_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": f"{pk['source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s"
+                               + (" x 0.5 (tf32 rate)" if args.precision in ("fp32", "tf32") else ""),
+                "avg_launch_us": avg_launch_s * 1e6, "launches": int(dil_n),
+                "share_of_step": dil_ms / ms if ms else None,
+                "hbm_frac_whole_step": ALGO_BYTES_PER_IMAGE_1024 * (S * S / 1048576.0) * (value / world) / (pk["hbm_gbs"] * 1e9),
+                "stage_ms_per_step": {"stem": stem_ms / args.steps, "dilated": dil_ms / args.steps,
+                                      "head": head_ms / args.steps, "ccl": ccl_ms / args.steps}}
+        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+                "data": "synthetic", "config": cfg, "clocks": clk.summary(),
+                "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(imgs.nbytes),
+                        "d2h_bytes_per_step": int(mask_h.nbytes + 4 * B + 72 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum())}
+        if world == 1 and not args.no_cpu_baseline:
+            v, step_s, cores = time_cpu(weights, imgs[:args.cpu_sample], thr, 3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
+                                    "sample": f"3 steps x {args.cpu_sample} images of {S}x{S} (torch-CPU restatement + cv2)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

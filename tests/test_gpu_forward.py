@@ -1,0 +1,123 @@
+"""-m gpu: CUDA forward pass vs the CPU oracle, through the C ABI (ubd_forward).
+Tolerance (north_star): |sigmoid(logit) - sigmoid(oracle logit)| <= 1e-3 for fp32 / tf32."""
+import numpy as np
+import pytest
+
+from oracle import net as onet
+from ubdvss_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = {"fp32": 1e-3, "tf32": 1e-3, "bf16": 3e-2}
+
+
+def _sig(z):
+    return 1.0 / (1.0 + np.exp(-z.astype(np.float64)))
+
+
+def _engine(**kw):
+    from ubdvss_b200.engine import Engine
+    return Engine(**kw)
+
+
+def _check(eng, w, x, pre, fml=True, precision="fp32"):
+    got = eng.forward(x, pre)
+    xin = x.astype(np.float64)
+    if pre == _lib.PREPROC_MOBILENET:
+        xin = onet.preprocess(xin, "mobilenet_like")
+    ref = onet.forward_torch(w, xin.astype(np.float32), fml_compatible=fml)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    dp = np.abs(_sig(got[..., 0]) - _sig(ref[..., 0])).max()
+    assert dp <= PROB_TOL[precision], dp
+    if precision == "fp32":
+        assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    return got, ref
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_config_a_parity(precision):
+    """BASELINE configs[0]: 8 x 512x512 grayscale, random-init weights."""
+    w = onet.init_weights(0, seed=1234)
+    eng = _engine(precision=precision)
+    eng.set_weights(w)
+    x = synth.synth_images(8, 512, 512, seed=0)
+    _check(eng, w, x, _lib.PREPROC_MOBILENET, precision=precision)
+    xf = (x.astype(np.float32) - 127.5) / 127.5
+    _check(eng, w, xf, _lib.PREPROC_NONE, precision=precision)
+
+
+@pytest.mark.parametrize("fml", [True, False])
+@pytest.mark.parametrize("n_classes,grey", [(0, True), (6, True), (26, True), (3, False)])
+def test_variants(fml, n_classes, grey):
+    w = onet.init_weights(n_classes, seed=5, grey=grey)
+    eng = _engine(grey=grey, fml_compatible=fml, n_classes=n_classes)
+    eng.set_weights(w)
+    x = synth.synth_images(3, 64, 192, seed=2, channels=1 if grey else 3)
+    got, ref = _check(eng, w, x, _lib.PREPROC_MOBILENET, fml=fml)
+    assert got.shape == (3, 16, 48, 1 + n_classes)
+    assert np.abs(got - ref).max() <= 1e-4
+
+
+def test_ragged_and_large_shapes():
+    """Non-square, sides that are multiples of 16 but not of 64, and the 2176x3840 scan (config C)."""
+    w = onet.init_weights(0, seed=9)
+    eng = _engine()
+    eng.set_weights(w)
+    for shape in [(1, 16, 16), (2, 48, 80), (1, 144, 400)]:
+        x = synth.synth_images(shape[0], shape[1], shape[2], seed=4)
+        _check(eng, w, x, _lib.PREPROC_NONE)
+    x = synth.synth_images(1, 2176, 3840, seed=5)
+    _check(eng, w, x, _lib.PREPROC_MOBILENET)
+
+
+def test_chunking_is_invisible():
+    w = onet.init_weights(2, seed=3)
+    eng = _engine(n_classes=2)
+    eng.set_weights(w)
+    x = synth.synth_images(7, 64, 64, seed=8)
+    a = eng.forward(x, _lib.PREPROC_MOBILENET)
+    eng.set_option("chunk", 3)
+    b = eng.forward(x, _lib.PREPROC_MOBILENET)
+    assert np.array_equal(a, b)
+
+
+def test_identity_and_delta_known_answers():
+    """identity kernels pass maps through; a delta weight pins tap orientation."""
+    w = onet.init_weights(0, seed=3)
+    for li in range(6):
+        k = np.zeros((3, 3, 24, 24), np.float32)
+        k[1, 1, np.arange(24), np.arange(24)] = 1
+        w[9 + 2 * li] = k
+        w[10 + 2 * li] = np.zeros(24, np.float32)
+    hk = np.zeros((1, 1, 24, 1), np.float32); hk[0, 0, 7, 0] = 1
+    w[21] = hk; w[22] = np.zeros(1, np.float32)
+    eng = _engine()
+    eng.set_weights(w)
+    x = synth.synth_images(1, 128, 128, seed=1)
+    got = eng.forward(x, _lib.PREPROC_MOBILENET)
+    _, acts = onet.forward_numpy(w, onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32), return_all=True)
+    assert np.abs(got[..., 0] - acts[2][..., 7]).max() <= 1e-5
+    # one off-centre tap at dilation 16 (layer L8): output = input shifted by (+16, -16)
+    k = np.zeros((3, 3, 24, 24), np.float32); k[2, 0, np.arange(24), np.arange(24)] = 1
+    w[9 + 2 * 4] = k
+    eng.set_weights(w)
+    got = eng.forward(x, _lib.PREPROC_MOBILENET)
+    src = acts[2][0, :, :, 7]
+    exp = np.zeros_like(src); exp[:-16, 16:] = src[16:, :-16]
+    assert np.abs(got[0, :, :, 0] - exp).max() <= 1e-5
+
+
+def test_weight_roundtrip_and_errors():
+    w = onet.init_weights(4, seed=11)
+    eng = _engine(n_classes=4)
+    with pytest.raises(_lib.UbdError) as e:
+        eng.forward(np.zeros((1, 64, 64, 1), np.uint8))
+    assert e.value.code == -3
+    eng.set_weights(w)
+    for a, b in zip(w, eng.get_weights()):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        eng.set_weights(w[:-1])
+    with pytest.raises(_lib.UbdError) as e:
+        eng.forward(np.zeros((1, 40, 64, 1), np.uint8))       # 40 is not a multiple of 16
+    assert e.value.code == -1

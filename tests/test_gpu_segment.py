@@ -1,0 +1,108 @@
+"""-m gpu: the reference-facing operator (ModelRunner.predict / SegmapManager.postprocess /
+get_contours_and_boxes) end to end vs the oracle and the reference-made fixtures."""
+import numpy as np
+import pytest
+
+from oracle import net as onet
+from oracle import postproc as pp
+from ubdvss_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+class _FakeModel:
+    def __init__(self, logits):
+        self._l = logits
+
+    def predict(self, images):
+        return self._l
+
+
+def _cfg(n_classes=0, min_area=5):
+    from ubdvss_b200.net import NetConfig
+    cfg = NetConfig(min_pixels_for_detection=min_area)
+    if n_classes:
+        cfg.set_class_names([f"type{i}" for i in range(n_classes)])
+    return cfg
+
+
+@pytest.mark.parametrize("thr", [50, 70])
+@pytest.mark.parametrize("mode", ["det", "cls"])
+def test_model_runner_predict_matches_reference_golden(golden, thr, mode):
+    from ubdvss_b200.model_runner import ModelRunner
+    logits = golden["predict_logits"].astype(np.float32)
+    runner = ModelRunner(_cfg(3 if mode == "cls" else 0), pixel_threshold=thr / 100)
+    assert float(runner._logit_threshold) == float(golden[f"logit_threshold_{thr}"])
+    det, cls, found = runner.predict(_FakeModel(logits), None)
+    key = f"predict_t{thr}_{mode}"
+    assert det.shape == logits.shape[:3] + (1,) and np.array_equal(det.astype(np.uint8), golden[f"{key}_mask"])
+    assert np.array_equal(cls, logits[..., 1:])
+    assert [len(f) for f in found] == list(golden[f"{key}_counts"])
+    boxes = [o.bbox for f in found for o in f]
+    bad = sum(not pp.boxes_equivalent(b, g) for b, g in zip(boxes, golden[f"{key}_boxes"]))
+    assert bad <= 1
+    if mode == "cls":
+        assert [o.object_type for f in found for o in f] == list(golden[f"{key}_classes"])
+
+
+@pytest.mark.parametrize("n_classes", [0, 4])
+def test_end_to_end_against_oracle(n_classes):
+    """net + threshold + CC + boxes through B200Model/ModelRunner vs torch-CPU oracle + cv2."""
+    from ubdvss_b200.model_runner import ModelRunner
+    from ubdvss_b200.net import B200Model
+    w = onet.init_weights(n_classes, seed=1234)
+    cfg = _cfg(n_classes)
+    model = B200Model(cfg, weights=w)
+    x = synth.synth_images(4, 256, 320, seed=21)
+    xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
+    ref_logits = onet.forward_torch(w, xf)
+    # pick the threshold so that ~10 % of the pixels are positive (random-init logits)
+    p_thr = float(1 / (1 + np.exp(-np.quantile(ref_logits[..., 0], 0.9))))
+    runner = ModelRunner(cfg, pixel_threshold=p_thr)
+    det, cls, found = runner.predict(model, x, preprocessing="mobilenet_like")
+    # probability maps within 1e-3; labels/boxes bit-exact ON THE IDENTICAL MASK the GPU produced
+    logits = model.predict(x, preprocessing="mobilenet_like")
+    sig = lambda z: 1 / (1 + np.exp(-z.astype(np.float64)))
+    assert np.abs(sig(logits[..., 0]) - sig(ref_logits[..., 0])).max() <= 1e-3
+    assert np.array_equal(det, pp.threshold_mask(logits[..., :1], runner._logit_threshold))
+    assert np.mean(det != pp.threshold_mask(ref_logits[..., :1], runner._logit_threshold)) < 1e-3
+    assert det.dtype == np.int64 and 0.02 < det.mean() < 0.3
+    for i in range(x.shape[0]):
+        ref = pp.postprocess_cv2(det[i], logits[i, ..., 1:] if n_classes else None, scale=4, min_area_threshold=5)
+        assert len(found[i]) == len(ref)
+        for o, (b, c) in zip(found[i], ref):
+            assert pp.boxes_equivalent(o.bbox, b, tol=0) or pp.boxes_equivalent(o.bbox, b, tol=4)
+            if n_classes:
+                assert o.object_type == c
+    # float input = already preprocessed (Keras semantics): same result
+    det2, _, _ = runner.predict(model, xf)
+    assert np.mean(det2 != det) < 1e-4
+
+
+def test_postprocess_and_contours_api(golden):
+    from ubdvss_b200.segmap_manager import SegmapManager
+    from ubdvss_b200.utils import get_contours_and_boxes
+    masks = golden["m64x96_masks"]
+    fb = golden["m64x96_float_boxes"]
+    o = 0
+    for i in range(masks.shape[0]):
+        objs = SegmapManager.postprocess(masks[i][..., None].astype(np.int64), None, scale=4, min_area_threshold=5)
+        cnts, boxes = get_contours_and_boxes(masks[i], min_area=5)
+        n = int(golden["m64x96_float_counts"][i])
+        assert len(objs) == len(boxes) == n
+        for b, g in zip(boxes, fb[o:o + n]):
+            assert b.dtype == np.float32 and b.shape == (8,)
+            assert pp.boxes_equivalent(np.round(b * 4), np.round(g * 4), tol=4)
+        assert [int(c["area_x2"]) for c in cnts] == list(golden["m64x96_kept_area_x2"][o:o + n])
+        o += n
+
+
+def test_rescale():
+    from ubdvss_b200.data_markup import ClassifiedObjectMarkup, ObjectMarkup
+    from ubdvss_b200.model_runner import ModelRunner
+
+    class MI:
+        xscale, yscale = 2.0, 0.5
+    found = [[ObjectMarkup(np.arange(8)), ClassifiedObjectMarkup(np.arange(8) + 1, 3)]]
+    out = ModelRunner.rescale(found, [MI()])
+    assert list(out[0][0].bbox) == [0, 0, 4, 1, 8, 2, 12, 3] and out[0][1].object_type == 3

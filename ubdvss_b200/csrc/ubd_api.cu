@@ -1,0 +1,540 @@
+// libubd.so: C ABI (include/ubd.h) over the sm_100a kernels.  Host orchestration only: workspace
+// management, chunking of the batch so that inter-layer feature maps stay L2-resident, launches.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ubd_ccl.cuh"
+#include "ubd_common.cuh"
+#include "ubd_fp32.cuh"
+#include "ubd_handle.cuh"
+#include "ubd_tc.cuh"
+#include "ubd_train.cuh"
+
+static std::string g_create_error;
+
+#define LAUNCH_CHECK()                                                     \
+  do {                                                                     \
+    ++h->launches;                                                         \
+    cudaError_t e_ = cudaGetLastError();                                   \
+    if (e_ != cudaSuccess) {                                               \
+      h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);    \
+      return UBD_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+
+// CUDA-event bracket of a kernel group on the handle's stream; resolved lazily at the next sync.
+struct ProfScope {
+  ubd_handle h; ubd_handle_s::Prof* p; cudaEvent_t a = nullptr, b = nullptr; int n0;
+  ProfScope(ubd_handle h_, ubd_handle_s::Prof* p_) : h(h_), p(p_), n0((int)h_->launches) {
+    if (!h->profile) return;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, h->stream);
+  }
+  ~ProfScope() {
+    if (!h->profile) return;
+    cudaEventRecord(b, h->stream);
+    p->launches += h->launches - n0;
+    h->pending.push_back({p, {a, b}});
+  }
+};
+static void resolve_profile(ubd_handle h) {
+  for (auto& e : h->pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(e.second.second);
+    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    e.first->ms += ms;
+    cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+  }
+  h->pending.clear();
+}
+
+static int ensure(ubd_handle h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return UBD_OK;
+  if (b.p) { UBD_CUDA(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + (bytes >> 3);
+  UBD_CUDA(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return UBD_OK;
+}
+#define ENSURE(buf, bytes) do { int rc_ = ensure(h, (buf), (bytes)); if (rc_) return rc_; } while (0)
+
+extern "C" int ubd_version(void) { return 100; }
+
+extern "C" int ubd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char* ubd_last_error(ubd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classes, int precision, ubd_handle* out) {
+  if (!out) { g_create_error = "ubd_create: out is NULL"; return UBD_ERR_ARG; }
+  *out = nullptr;
+  if (n_classes < 0 || n_classes > UBD_MAX_CLASSES) { g_create_error = "ubd_create: n_classes out of range"; return UBD_ERR_ARG; }
+  if (precision < UBD_FP32 || precision > UBD_BF16) { g_create_error = "ubd_create: unknown precision"; return UBD_ERR_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = "ubd_create: no CUDA device visible (libubd has no CPU fallback)";
+    return UBD_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "ubd_create: device index out of range"; return UBD_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return UBD_ERR_CUDA; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "ubd_create: libubd is built for sm_100a (B200) only; device is sm_" +
+                     std::to_string(prop.major) + std::to_string(prop.minor);
+    return UBD_ERR_UNSUPPORTED;
+  }
+  ubd_handle h = new ubd_handle_s();
+  h->device = device; h->grey = grey != 0; h->fml = fml_compatible != 0; h->n_classes = n_classes;
+  h->precision = precision; h->spec = make_weight_spec(grey, n_classes);
+  h->n_sm = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  h->stream = h->own_stream;
+  if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return UBD_ERR_CUDA; }
+  // preprocessing table for uint8 input: exactly what numpy computes, (v - 127.5) / 127.5 in
+  // float64 (net.py:217-218 on a uint8 image) then cast to float32 at the Keras boundary
+  float lut[256];
+  for (int v = 0; v < 256; ++v) lut[v] = (float)(((double)v - 127.5) / 127.5);
+  if (cudaMalloc(&h->d_lut, sizeof(lut)) != cudaSuccess ||
+      cudaMemcpy(h->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess) {
+    g_create_error = "ubd_create: cudaMalloc failed"; delete h; return UBD_ERR_CUDA;
+  }
+  size_t wbytes = (size_t)h->spec.total * sizeof(float);
+  if (cudaMalloc(&h->d_params, wbytes) != cudaSuccess) { g_create_error = "ubd_create: cudaMalloc failed"; delete h; return UBD_ERR_CUDA; }
+  cudaFuncSetAttribute(dilconv_fp32_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
+  cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
+  cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
+  tc_setup_attributes();
+  *out = h;
+  return UBD_OK;
+}
+
+extern "C" int ubd_destroy(ubd_handle h) {
+  if (!h) return UBD_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : h->all_bufs()) if (b->p) cudaFree(b->p);
+  if (h->d_params) cudaFree(h->d_params);
+  if (h->d_lut) cudaFree(h->d_lut);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  resolve_profile(h);
+  cudaStreamDestroy(h->own_stream);
+  delete h;
+  return UBD_OK;
+}
+
+extern "C" int ubd_synchronize(ubd_handle h) {
+  if (!h) return UBD_ERR_ARG;
+  UBD_CUDA(cudaSetDevice(h->device));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  return UBD_OK;
+}
+
+extern "C" int64_t ubd_launch_count(ubd_handle h) { return h ? h->launches : 0; }
+
+extern "C" int ubd_set_stream(ubd_handle h, void* cuda_stream) {
+  if (!h) return UBD_ERR_ARG;
+  UBD_CUDA(cudaSetDevice(h->device));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return UBD_OK;
+}
+
+extern "C" int ubd_get_stat(ubd_handle h, const char* name, double* value) {
+  if (!h || !name || !value) return UBD_ERR_ARG;
+  resolve_profile(h);
+  if (!strcmp(name, "launches")) *value = (double)h->launches;
+  else if (!strcmp(name, "dilconv_ms")) *value = h->prof_dil.ms;
+  else if (!strcmp(name, "dilconv_launches")) *value = (double)h->prof_dil.launches;
+  else if (!strcmp(name, "stem_ms")) *value = h->prof_stem.ms;
+  else if (!strcmp(name, "stem_launches")) *value = (double)h->prof_stem.launches;
+  else if (!strcmp(name, "head_ms")) *value = h->prof_head.ms;
+  else if (!strcmp(name, "ccl_ms")) *value = h->prof_ccl.ms;
+  else if (!strcmp(name, "ccl_launches")) *value = (double)h->prof_ccl.launches;
+  else UBD_FAIL(UBD_ERR_ARG, std::string("unknown stat ") + name);
+  return UBD_OK;
+}
+
+extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
+  if (!h || !name) return UBD_ERR_ARG;
+  if (!strcmp(name, "chunk")) { if (value < 0) UBD_FAIL(UBD_ERR_ARG, "chunk must be >= 0"); h->opt_chunk = (int)value; }
+  else if (!strcmp(name, "max_comps")) { if (value < 1) UBD_FAIL(UBD_ERR_ARG, "max_comps must be >= 1"); h->opt_max_comps = (int)value; }
+  else if (!strcmp(name, "max_points")) { if (value < 1) UBD_FAIL(UBD_ERR_ARG, "max_points must be >= 1"); h->opt_max_points = (int)value; }
+  else if (!strcmp(name, "profile")) {
+    resolve_profile(h);
+    h->profile = value != 0;
+    h->prof_dil = h->prof_stem = h->prof_ccl = h->prof_head = ubd_handle_s::Prof();
+  }
+  else if (!strcmp(name, "precision")) { if (value < UBD_FP32 || value > UBD_BF16) UBD_FAIL(UBD_ERR_ARG, "bad precision"); h->precision = (int)value; }
+  else UBD_FAIL(UBD_ERR_ARG, std::string("unknown option ") + name);
+  return UBD_OK;
+}
+
+static int check_weight_args(ubd_handle h, const void* arrays, const int64_t* n_elems, int n_arrays) {
+  if (!arrays || !n_elems) UBD_FAIL(UBD_ERR_ARG, "weights: NULL argument");
+  if (n_arrays != UBD_N_WEIGHT_ARRAYS) UBD_FAIL(UBD_ERR_ARG, "weights: expected 23 arrays (Keras get_weights() order)");
+  for (int i = 0; i < n_arrays; ++i)
+    if (n_elems[i] != h->spec.size[i])
+      UBD_FAIL(UBD_ERR_ARG, "weights: array " + std::to_string(i) + " has " + std::to_string(n_elems[i]) +
+                                " elements, expected " + std::to_string(h->spec.size[i]));
+  return UBD_OK;
+}
+
+extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const int64_t* n_elems, int n_arrays) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_weight_args(h, arrays, n_elems, n_arrays);
+  if (rc) return rc;
+  UBD_CUDA(cudaSetDevice(h->device));
+  std::vector<float> flat(h->spec.total);
+  for (int i = 0; i < n_arrays; ++i) {
+    if (!arrays[i]) UBD_FAIL(UBD_ERR_ARG, "weights: NULL array");
+    memcpy(flat.data() + h->spec.off[i], arrays[i], h->spec.size[i] * sizeof(float));
+  }
+  UBD_CUDA(cudaMemcpyAsync(h->d_params, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  h->have_weights = true;
+  h->tc_weights_dirty = true;
+  return UBD_OK;
+}
+
+extern "C" int ubd_get_weights(ubd_handle h, float* const* arrays, const int64_t* n_elems, int n_arrays) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_weight_args(h, arrays, n_elems, n_arrays);
+  if (rc) return rc;
+  if (!h->have_weights) UBD_FAIL(UBD_ERR_NO_WEIGHTS, "get_weights before set_weights");
+  UBD_CUDA(cudaSetDevice(h->device));
+  std::vector<float> flat(h->spec.total);
+  UBD_CUDA(cudaMemcpyAsync(flat.data(), h->d_params, flat.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_arrays; ++i) memcpy(arrays[i], flat.data() + h->spec.off[i], h->spec.size[i] * sizeof(float));
+  return UBD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+
+static int check_image_args(ubd_handle h, const void* images, int in_dtype, int n, int H, int W, int preproc) {
+  if (!images) UBD_FAIL(UBD_ERR_ARG, "images is NULL");
+  if (in_dtype != UBD_U8 && in_dtype != UBD_F32) UBD_FAIL(UBD_ERR_ARG, "in_dtype must be UBD_U8 or UBD_F32");
+  if (preproc != UBD_PREPROC_NONE && preproc != UBD_PREPROC_MOBILENET) UBD_FAIL(UBD_ERR_ARG, "unknown preprocessing");
+  if (n < 1 || H < 16 || W < 16 || (H % 16) || (W % 16))
+    UBD_FAIL(UBD_ERR_ARG, "image sides must be positive multiples of 16 (reference feeds multiples of 64, segmap_manager.py:153-165)");
+  if (!h->have_weights) UBD_FAIL(UBD_ERR_NO_WEIGHTS, "no weights loaded (ubd_set_weights)");
+  return UBD_OK;
+}
+
+static size_t image_bytes(ubd_handle h, int in_dtype, int n, int H, int W) {
+  return (size_t)n * H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
+}
+
+// Separable layer launcher (L1: raw image; L2/L3: planar maps).
+template <int CIN, int STRIDE, bool RAW, typename TIn>
+static int launch_sep(ubd_handle h, const TIn* in, float4* out, int layer, int n, int H, int W, int Ho, int Wo,
+                      int pad_t, int pad_l, const float* lut, float pre_scale, float pre_shift) {
+  const float* base = h->d_params;
+  const float* dwk = base + h->spec.off[3 * layer];
+  const float* pwk = base + h->spec.off[3 * layer + 1];
+  const float* b = base + h->spec.off[3 * layer + 2];
+  dim3 grid((Wo + 31) / 32, (Ho + 3) / 4, n), block(128);
+  sep_layer_kernel<CIN, STRIDE, RAW, TIn><<<grid, block, 0, h->stream>>>(in, out, dwk, pwk, b, lut, pre_scale, pre_shift,
+                                                                        n, H, W, Ho, Wo, pad_t, pad_l);
+  LAUNCH_CHECK();
+  return UBD_OK;
+}
+
+// TF 'same' stride-2 padding before the image for even sizes is 0; FML pads 1 (net.py:229-232).
+static inline int stride2_pad(ubd_handle h) { return h->fml ? 1 : 0; }
+
+static int run_stem(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W,
+                    float4* act1, float4* act2, float4* act3) {
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+  const int p2 = stride2_pad(h);
+  const bool mob = preproc == UBD_PREPROC_MOBILENET;
+  int rc;
+  if (h->spec.cin == 1) {
+    if (in_dtype == UBD_U8)
+      rc = launch_sep<1, 2, true, uint8_t>(h, (const uint8_t*)d_img, act1, 0, n, H, W, H2, W2, p2, p2, mob ? h->d_lut : nullptr, 0.f, 0.f);
+    else
+      rc = launch_sep<1, 2, true, float>(h, (const float*)d_img, act1, 0, n, H, W, H2, W2, p2, p2, nullptr, mob ? 127.5f : 0.f, 127.5f);
+  } else {
+    if (in_dtype == UBD_U8)
+      rc = launch_sep<3, 2, true, uint8_t>(h, (const uint8_t*)d_img, act1, 0, n, H, W, H2, W2, p2, p2, mob ? h->d_lut : nullptr, 0.f, 0.f);
+    else
+      rc = launch_sep<3, 2, true, float>(h, (const float*)d_img, act1, 0, n, H, W, H2, W2, p2, p2, nullptr, mob ? 127.5f : 0.f, 127.5f);
+  }
+  if (rc) return rc;
+  rc = launch_sep<24, 1, false, float>(h, (const float*)act1, act2, 1, n, H2, W2, H2, W2, 1, 1, nullptr, 0.f, 0.f);
+  if (rc) return rc;
+  rc = launch_sep<24, 2, false, float>(h, (const float*)act2, act3, 2, n, H2, W2, H4, W4, p2, p2, nullptr, 0.f, 0.f);
+  return rc;
+}
+
+static int launch_dil_fp32(ubd_handle h, const float4* in, float4* out, const float* w, const float* b,
+                           const float4* gate, int n, int hh, int ww, int d, int mode) {
+  dim3 grid((ww + DIL_TW - 1) / DIL_TW, (hh + DIL_TH - 1) / DIL_TH, n), block(128);
+  const size_t smem = 9 * 24 * 24 * 4;
+  if (mode == 0) dilconv_fp32_kernel<true, true, false><<<grid, block, smem, h->stream>>>(in, out, w, b, nullptr, n, hh, ww, d);
+  else if (mode == 1) dilconv_fp32_kernel<false, false, true><<<grid, block, smem, h->stream>>>(in, out, w, nullptr, gate, n, hh, ww, d);
+  else dilconv_fp32_kernel<false, false, false><<<grid, block, smem, h->stream>>>(in, out, w, nullptr, nullptr, n, hh, ww, d);
+  LAUNCH_CHECK();
+  return UBD_OK;
+}
+
+static int launch_head(ubd_handle h, const float4* in, float* logits, uint8_t* mask, float thr, int n, int hh, int ww) {
+  const float* hk = h->d_params + h->spec.off[21];
+  const float* hb = h->d_params + h->spec.off[22];
+  dim3 grid((unsigned)(((size_t)hh * ww + 127) / 128), n), block(128);
+  head_threshold_kernel<<<grid, block, 0, h->stream>>>(in, logits, mask, hk, hb, h->spec.n_out, thr, n, hh, ww);
+  LAUNCH_CHECK();
+  return UBD_OK;
+}
+
+static int pick_chunk(ubd_handle h, int n, int H, int W) {
+  if (h->opt_chunk > 0) return std::min(n, h->opt_chunk);
+  // keep the two ping-pong quarter-resolution maps (+ the stem's half-resolution maps) of one chunk
+  // inside the ~126 MB L2: 2 * 96 B/px at H/4 + 2 * 96 B/px at H/2 per image
+  const double per_img = (double)H * W * (2.0 * 96 / 16 + 2.0 * 96 / 4);
+  int c = (int)(96e6 / per_img);
+  return std::max(1, std::min(n, c));
+}
+
+// d_img: device images.  d_logits (nullable) / d_mask (nullable): device outputs for the whole batch.
+static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
+                          float* d_logits, uint8_t* d_mask, float thr) {
+  const int h4 = H / 4, w4 = W / 4;
+  const int chunk = pick_chunk(h, n, H, W);
+  const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
+  ENSURE(h->act1, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
+  ENSURE(h->act2, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
+  ENSURE(h->mapA, (size_t)chunk * UBD_NG * q_px * sizeof(float4));
+  ENSURE(h->mapB, (size_t)chunk * UBD_NG * q_px * sizeof(float4));
+  const size_t img_stride = (size_t)H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int cn = std::min(chunk, n - c0);
+    const char* img = (const char*)d_img + (size_t)c0 * img_stride;
+    float4* A = (float4*)h->mapA.p;
+    float4* B = (float4*)h->mapB.p;
+    int rc;
+    { ProfScope ps(h, &h->prof_stem); rc = run_stem(h, img, in_dtype, preproc, cn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, A); }
+    if (rc) return rc;
+    for (int l = 0; l < UBD_NLAYERS_DIL; ++l) {
+      ProfScope ps(h, &h->prof_dil);
+      const float* w = h->d_params + h->spec.off[9 + 2 * l];
+      const float* b = h->d_params + h->spec.off[10 + 2 * l];
+      if (h->precision == UBD_FP32) rc = launch_dil_fp32(h, A, B, w, b, nullptr, cn, h4, w4, kDilations[l], 0);
+      else rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l]);
+      if (rc) return rc;
+      std::swap(A, B);
+    }
+    { ProfScope ps(h, &h->prof_head);
+      rc = launch_head(h, A, d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
+                       d_mask ? d_mask + (size_t)c0 * q_px : nullptr, thr, cn, h4, w4); }
+    if (rc) return rc;
+  }
+  return UBD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// connected components on device mask -> host component list
+// ------------------------------------------------------------------------------------------------
+
+static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, int cls_stride, int n_cls,
+                      int n, int mh, int mw, int min_area_x2, int32_t* labels_out_host,
+                      ubd_component* comps_out, int max_out, int32_t* n_comps_per_image) {
+  const size_t npx = (size_t)mh * mw;
+  const size_t pstride = (npx + 1 + 31) & ~(size_t)31;
+  const int max_comps = h->opt_max_comps;
+  const int max_pts = h->opt_max_points > 0 ? h->opt_max_points : (int)std::min<size_t>((size_t)n * npx / 2 + 1024, (size_t)1 << 26);
+  ENSURE(h->parent, (size_t)n * pstride * sizeof(int));
+  ENSURE(h->labels, (size_t)n * npx * sizeof(int));
+  ENSURE(h->slot_of, (size_t)n * npx * sizeof(int));
+  ENSURE(h->comps, (size_t)n * max_comps * sizeof(CompRec));
+  ENSURE(h->cls_sums, (size_t)n * max_comps * std::max(n_cls, 1) * sizeof(unsigned long long));
+  ENSURE(h->n_comps, (size_t)(2 * n) * sizeof(int) + sizeof(CclTotals));
+  ENSURE(h->out_recs, (size_t)std::max(max_out, 1) * sizeof(OutRec));
+  ENSURE(h->out_index, (size_t)n * max_comps * sizeof(int));
+  ENSURE(h->hull_pts, (size_t)max_pts * sizeof(HullPt));
+  int* d_ncomps = (int*)h->n_comps.p;
+  int* d_kept = d_ncomps + n;
+  CclTotals* d_tot = (CclTotals*)(d_kept + n);
+  int* parent = (int*)h->parent.p;
+  int* labels = (int*)h->labels.p;
+  int* slot_of = (int*)h->slot_of.p;
+  CompRec* comps = (CompRec*)h->comps.p;
+  unsigned long long* cls_sums = (unsigned long long*)h->cls_sums.p;
+
+  dim3 tgrid((mw + 31) / 32, (mh + 7) / 8, n), tblock(256);
+  dim3 lgrid((unsigned)((npx + 1 + 255) / 256), n);
+  ProfScope* ps_ccl = new ProfScope(h, &h->prof_ccl);
+  UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
+  ccl_init_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_merge1_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, labels, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_slots_kernel<<<n, 1024, 0, h->stream>>>(labels, slot_of, comps, cls_sums, n_cls, d_ncomps, mh, mw, max_comps); LAUNCH_CHECK();
+  dim3 sgrid((mw + 1 + 31) / 32, (mh + 1 + 7) / 8, n);
+  ccl_stats_kernel<<<sgrid, tblock, 0, h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls, mh, mw, max_comps); LAUNCH_CHECK();
+  ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
+  ccl_compact_kernel<<<n, 256, 0, h->stream>>>(comps, cls_sums, n_cls, d_ncomps, d_kept, (OutRec*)h->out_recs.p,
+                                               (int*)h->out_index.p, max_comps, max_out, min_area_x2); LAUNCH_CHECK();
+  ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)h->hull_pts.p,
+                                                     d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();
+  delete ps_ccl;
+
+  // header: kept counts per image + totals (one small D2H), then the records and hull points
+  std::vector<int> header(n + sizeof(CclTotals) / sizeof(int));
+  UBD_CUDA(cudaMemcpyAsync(header.data(), d_kept, header.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (labels_out_host)
+    UBD_CUDA(cudaMemcpyAsync(labels_out_host, labels, (size_t)n * npx * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  CclTotals tot;
+  memcpy(&tot, header.data() + n, sizeof(tot));
+  if (tot.max_ncomp > max_comps)
+    UBD_FAIL(UBD_ERR_OVERFLOW, "an image has " + std::to_string(tot.max_ncomp) + " components > max_comps option " +
+                                   std::to_string(max_comps) + " (ubd_set_option \"max_comps\")");
+  if (tot.total_kept > max_out)
+    UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_kept) + " kept components exceed the caller's capacity " + std::to_string(max_out));
+  if (tot.total_pts > max_pts)
+    UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_pts) + " hull candidate points exceed max_points " + std::to_string(max_pts));
+  for (int i = 0; i < n; ++i) n_comps_per_image[i] = header[i];
+  if (tot.total_kept == 0) return UBD_OK;
+  std::vector<OutRec> recs(tot.total_kept);
+  std::vector<HullPt> pts(tot.total_pts);
+  UBD_CUDA(cudaMemcpyAsync(recs.data(), h->out_recs.p, recs.size() * sizeof(OutRec), cudaMemcpyDeviceToHost, h->stream));
+  if (!pts.empty())
+    UBD_CUDA(cudaMemcpyAsync(pts.data(), h->hull_pts.p, pts.size() * sizeof(HullPt), cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  // group the hull candidates by component (counting sort), then boxes on the host
+  std::vector<int> start(tot.total_kept + 1, 0);
+  for (const HullPt& p : pts) start[p.comp + 1]++;
+  for (int i = 0; i < tot.total_kept; ++i) start[i + 1] += start[i];
+  std::vector<int32_t> xy(2 * pts.size());
+  std::vector<int> fill(start.begin(), start.end() - 1);
+  for (const HullPt& p : pts) {
+    const int k = fill[p.comp]++;
+    xy[2 * k] = p.xy & 0xffff; xy[2 * k + 1] = p.xy >> 16;
+  }
+  for (int i = 0; i < tot.total_kept; ++i) {
+    const OutRec& r = recs[i];
+    ubd_component& c = comps_out[i];
+    c.image = r.image; c.label = r.label; c.xmin = r.xmin; c.ymin = r.ymin; c.xmax = r.xmax; c.ymax = r.ymax;
+    c.n_pixels = r.n_pixels; c.n_filled = r.n_filled; c.area_x2 = r.area_x2; c.class_id = r.class_id;
+    ubd_min_area_box(xy.data() + 2 * start[i], start[i + 1] - start[i], c.box);
+  }
+  return UBD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// public inference entry points
+// ------------------------------------------------------------------------------------------------
+
+extern "C" int ubd_forward_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int H, int W, int preproc, float* d_logits) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_image_args(h, d_images, in_dtype, n, H, W, preproc);
+  if (rc) return rc;
+  if (!d_logits) UBD_FAIL(UBD_ERR_ARG, "d_logits is NULL");
+  UBD_CUDA(cudaSetDevice(h->device));
+  return forward_device(h, d_images, in_dtype, n, H, W, preproc, d_logits, nullptr, 0.f);
+}
+
+extern "C" int ubd_forward(ubd_handle h, const void* images, int in_dtype, int n, int H, int W, int preproc, float* logits_out) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_image_args(h, images, in_dtype, n, H, W, preproc);
+  if (rc) return rc;
+  if (!logits_out) UBD_FAIL(UBD_ERR_ARG, "logits_out is NULL");
+  UBD_CUDA(cudaSetDevice(h->device));
+  const size_t ib = image_bytes(h, in_dtype, n, H, W);
+  const size_t lb = (size_t)n * (H / 4) * (W / 4) * h->spec.n_out * sizeof(float);
+  ENSURE(h->d_images, ib);
+  ENSURE(h->d_logits, lb);
+  UBD_CUDA(cudaMemcpyAsync(h->d_images.p, images, ib, cudaMemcpyHostToDevice, h->stream));
+  rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, nullptr, 0.f);
+  if (rc) return rc;
+  UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, lb, cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  return UBD_OK;
+}
+
+static int segment_common(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
+                          float logit_thr, int min_area_x2, uint8_t* d_mask, float* d_logits,
+                          int32_t* labels_out_host, ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image) {
+  const int n_cls = h->n_classes;
+  int rc = forward_device(h, d_img, in_dtype, n, H, W, preproc, d_logits, d_mask, logit_thr);
+  if (rc) return rc;
+  return ccl_device(h, d_mask, n_cls ? d_logits + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4, min_area_x2,
+                    labels_out_host, comps_out, max_comps, n_comps_per_image);
+}
+
+extern "C" int ubd_segment_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int H, int W, int preproc,
+                               float logit_thr, int min_area_x2, uint8_t* d_mask, float* d_logits,
+                               ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_image_args(h, d_images, in_dtype, n, H, W, preproc);
+  if (rc) return rc;
+  if (!comps_out || !n_comps_per_image || max_comps < 0) UBD_FAIL(UBD_ERR_ARG, "component outputs are NULL");
+  UBD_CUDA(cudaSetDevice(h->device));
+  const size_t q = (size_t)n * (H / 4) * (W / 4);
+  if (!d_mask) { ENSURE(h->d_mask, q); d_mask = (uint8_t*)h->d_mask.p; }
+  if (!d_logits) { ENSURE(h->d_logits, q * h->spec.n_out * sizeof(float)); d_logits = (float*)h->d_logits.p; }
+  return segment_common(h, d_images, in_dtype, n, H, W, preproc, logit_thr, min_area_x2, d_mask, d_logits,
+                        nullptr, comps_out, max_comps, n_comps_per_image);
+}
+
+extern "C" int ubd_segment(ubd_handle h, const void* images, int in_dtype, int n, int H, int W, int preproc,
+                           float logit_thr, int min_area_x2, uint8_t* mask_out, float* logits_out, int32_t* labels_out,
+                           ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_image_args(h, images, in_dtype, n, H, W, preproc);
+  if (rc) return rc;
+  if (!comps_out || !n_comps_per_image || max_comps < 0) UBD_FAIL(UBD_ERR_ARG, "component outputs are NULL");
+  UBD_CUDA(cudaSetDevice(h->device));
+  const size_t ib = image_bytes(h, in_dtype, n, H, W);
+  const size_t q = (size_t)n * (H / 4) * (W / 4);
+  ENSURE(h->d_images, ib);
+  ENSURE(h->d_mask, q);
+  ENSURE(h->d_logits, q * h->spec.n_out * sizeof(float));
+  UBD_CUDA(cudaMemcpyAsync(h->d_images.p, images, ib, cudaMemcpyHostToDevice, h->stream));
+  // the mask / logits copies are queued before the component read-back so they overlap it
+  rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, (uint8_t*)h->d_mask.p, logit_thr);
+  if (rc) return rc;
+  if (mask_out) UBD_CUDA(cudaMemcpyAsync(mask_out, h->d_mask.p, q, cudaMemcpyDeviceToHost, h->stream));
+  if (logits_out) UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, q * h->spec.n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  const int n_cls = h->n_classes;
+  return ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4,
+                    min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
+}
+
+extern "C" int ubd_postprocess(ubd_handle h, const uint8_t* mask, const float* cls_logits, int n, int mh, int mw,
+                               int n_cls, int min_area_x2, int32_t* labels_out,
+                               ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image) {
+  if (!h) return UBD_ERR_ARG;
+  if (!mask || !comps_out || !n_comps_per_image) UBD_FAIL(UBD_ERR_ARG, "NULL argument");
+  if (n < 1 || mh < 1 || mw < 1 || mh > 65535 || mw > 65535) UBD_FAIL(UBD_ERR_ARG, "bad map shape");
+  if (n_cls < 0 || n_cls > UBD_MAX_CLASSES || (n_cls > 0 && !cls_logits)) UBD_FAIL(UBD_ERR_ARG, "bad class logits");
+  UBD_CUDA(cudaSetDevice(h->device));
+  const size_t q = (size_t)n * mh * mw;
+  ENSURE(h->d_mask, q);
+  UBD_CUDA(cudaMemcpyAsync(h->d_mask.p, mask, q, cudaMemcpyHostToDevice, h->stream));
+  if (n_cls > 0) {
+    ENSURE(h->d_logits, q * n_cls * sizeof(float));
+    UBD_CUDA(cudaMemcpyAsync(h->d_logits.p, cls_logits, q * n_cls * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  return ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p : nullptr, n_cls, n_cls, n, mh, mw,
+                    min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
+}
+
+#include "ubd_train_api.inc"

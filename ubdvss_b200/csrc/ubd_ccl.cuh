@@ -1,0 +1,395 @@
+// GPU connected components with cv2.findContours(RETR_EXTERNAL) semantics (utils.py:51-60,
+// segmap_manager.py:54-69; exact statement in SURVEY.md 8a/P2 and oracle/postproc.py::ccl_spec):
+//   1. union-find over all pixels: foreground 8-connected, background 4-connected, border
+//      background joined to a virtual outside node V = h*w;
+//   2. "filled" = foreground or background not in V's set (holes); union 8-adjacent filled pixels;
+//   3. label = root = smallest raster index of the filled component (first pixel in raster order);
+//   4. per-component reductions: bbox, foreground / filled pixel counts, 2x2 bit-quad counts
+//      (2*contourArea = 2*#Q4 + #Q3), class-probability sums over the filled pixels.
+// Unions always attach the larger root under the smaller one with atomicMin, so every parent
+// chain is strictly decreasing and the final root is the minimum index of the set.
+#pragma once
+#include "ubd_common.cuh"
+
+struct CompRec {            // device-side accumulator, one per component (slot order = raster order)
+  int label;
+  int xmin, ymin, xmax, ymax;
+  int n_pixels, n_filled;
+  int q3, q4;
+};
+
+__device__ __forceinline__ int uf_find(const int* parent, int i) {
+  int p;
+  while ((p = *((volatile const int*)(parent + i))) != i) i = p;
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }      // a > b: hang a under b
+    const int old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;                                      // a was no longer a root; retry from its parent
+  }
+}
+
+// parent[i] = start of the horizontal same-class run of i inside its 32-pixel warp segment
+// (ballot), so horizontal links inside a segment cost no atomics.
+__global__ void __launch_bounds__(256)
+ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (y >= h) return;
+  const uint8_t* m = mask + (size_t)n * h * w;
+  int* par = parent + (size_t)n * pstride;
+  const bool in = x < w;
+  const bool fg = in && m[(size_t)y * w + x] != 0;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned bits = __ballot_sync(0xffffffffu, fg);
+  if (in) {
+    const unsigned same = fg ? bits : ~bits;                 // lanes of my class
+    const unsigned below = (~same) & ((1u << lane) - 1u);    // other-class lanes left of me
+    const int start = below ? 32 - __clz(below) : 0;         // first lane of my run
+    par[(size_t)y * w + x] = y * w + (x - (int)lane + start);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) par[h * w] = h * w;   // outside node
+}
+
+// Phase 1: foreground 8-connectivity, background 4-connectivity (+ border background ~ outside).
+__global__ void __launch_bounds__(256)
+ccl_merge1_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const uint8_t* m = mask + (size_t)n * h * w;
+  int* par = parent + (size_t)n * pstride;
+  const int p = y * w + x;
+  const bool c = m[p] != 0;
+  const bool hasW = x > 0, hasN = y > 0, hasE = x < w - 1;
+  if (c) {
+    // decision tree: a present N neighbour already touches W, NW and NE, so one link suffices;
+    // W links inside a warp segment are implicit in ccl_init_kernel.
+    if (hasN && m[p - w] != 0) {
+      uf_union(par, p, p - w);
+    } else {
+      if (hasN && hasE && m[p - w + 1] != 0) uf_union(par, p, p - w + 1);
+      if (hasN && hasW && m[p - w - 1] != 0) uf_union(par, p, p - w - 1);
+      else if (hasW && (x & 31) == 0 && m[p - 1] != 0) uf_union(par, p, p - 1);
+    }
+  } else {
+    if (hasN && m[p - w] == 0) uf_union(par, p, p - w);
+    if (hasW && (x & 31) == 0 && m[p - 1] == 0) uf_union(par, p, p - 1);
+    if (!hasW || !hasN || !hasE || y == h - 1) uf_union(par, p, h * w);
+  }
+}
+
+// Full path compression: parent[p] = root(p) (also for the outside node).
+__global__ void __launch_bounds__(256)
+ccl_flatten_kernel(int* __restrict__ parent, int h, int w, size_t pstride) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > h * w) return;
+  int* par = parent + (size_t)n * pstride;
+  par[i] = uf_find(par, i);
+}
+
+// Phase 2: 8-connectivity over filled pixels.  Requires flattened parents from phase 1 (then a
+// non-root's parent never changes again and background p is outer iff parent[p] == parent[V]).
+// Pairs of two foreground pixels are already connected by phase 1 and are skipped.
+__global__ void __launch_bounds__(256)
+ccl_merge2_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const uint8_t* m = mask + (size_t)n * h * w;
+  int* par = parent + (size_t)n * pstride;
+  const int rootV = *((volatile int*)(par + h * w));
+  const int p = y * w + x;
+  const bool fg = m[p] != 0;
+  // a hole pixel's parent is either its (former) hole root or, if it is that root, something in
+  // its filled set; neither can equal rootV.
+  auto filled = [&](int q) -> bool { return m[q] != 0 || *((volatile int*)(par + q)) != rootV; };
+  if (!fg && !filled(p)) return;
+  const bool hasW = x > 0, hasN = y > 0, hasE = x < w - 1;
+  auto link = [&](int q) { if (!(fg && m[q] != 0)) uf_union(par, p, q); };
+  if (hasN && filled(p - w)) {
+    link(p - w);
+  } else {
+    if (hasN && hasE && filled(p - w + 1)) link(p - w + 1);
+    if (hasN && hasW && filled(p - w - 1)) link(p - w - 1);
+    else if (hasW && filled(p - 1)) link(p - 1);
+  }
+}
+
+// labels[p] = filled ? root : -1.
+__global__ void __launch_bounds__(256)
+ccl_label_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int* __restrict__ labels,
+                 int h, int w, size_t pstride) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  int* par = parent + (size_t)n * pstride;
+  const int rootV = uf_find(par, h * w);
+  const int r = uf_find(par, i);
+  const bool filled = mask[(size_t)n * h * w + i] != 0 || r != rootV;
+  labels[(size_t)n * h * w + i] = filled ? r : -1;
+}
+
+// One CTA per image: rank the roots in raster order -> slot_of[root], n_comps[n]; initialise records.
+__global__ void __launch_bounds__(1024)
+ccl_slots_kernel(const int* __restrict__ labels, int* __restrict__ slot_of, CompRec* __restrict__ comps,
+                 unsigned long long* __restrict__ cls_sums, int n_cls,
+                 int* __restrict__ n_comps, int h, int w, int max_comps) {
+  const int n = blockIdx.x;
+  const int* lab = labels + (size_t)n * h * w;
+  int* so = slot_of + (size_t)n * h * w;
+  CompRec* cr = comps + (size_t)n * max_comps;
+  __shared__ int warp_cnt[32];
+  __shared__ int warp_off[32];
+  __shared__ int chunk_total;
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i0 = 0; i0 < h * w; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool root = i < h * w && lab[i] == i;
+    const unsigned bits = __ballot_sync(0xffffffffu, root);
+    if (lane == 0) warp_cnt[wid] = __popc(bits);
+    __syncthreads();
+    if (wid == 0) {
+      const int own = lane < nwarps ? warp_cnt[lane] : 0;
+      int v = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      warp_off[lane] = v - own;
+      if (lane == 31) chunk_total = v;
+    }
+    __syncthreads();
+    if (root) {
+      const int slot = base + warp_off[wid] + __popc(bits & ((1u << lane) - 1u));
+      so[i] = slot;
+      if (slot < max_comps) {
+        CompRec r; r.label = i; r.xmin = w; r.ymin = h; r.xmax = -1; r.ymax = -1;
+        r.n_pixels = 0; r.n_filled = 0; r.q3 = 0; r.q4 = 0;
+        cr[slot] = r;
+        for (int c = 0; c < n_cls; ++c) cls_sums[((size_t)n * max_comps + slot) * n_cls + c] = 0ull;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_comps[n] = base;
+}
+
+__device__ __forceinline__ int group_sum(unsigned grp, int v) { return __reduce_add_sync(grp, v); }
+
+// Thread = one 2x2 window whose bottom-right pixel is (y,x), y in [0,h], x in [0,w]: contributes the
+// pixel (y,x) itself (bbox, counts, class probabilities) and the bit-quad of the window.
+// Lanes of a warp that hit the same component are combined first (match_any + redux).
+__global__ void __launch_bounds__(256)
+ccl_stats_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
+                 const int* __restrict__ slot_of, CompRec* __restrict__ comps,
+                 const float* __restrict__ cls_logits, int cls_stride,
+                 unsigned long long* __restrict__ cls_sums, int n_cls,
+                 int h, int w, int max_comps) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int* lab = labels + (size_t)n * h * w;
+  const int* so = slot_of + (size_t)n * h * w;
+  CompRec* cr = comps + (size_t)n * max_comps;
+  auto L = [&](int yy, int xx) -> int {
+    return (yy >= 0 && yy < h && xx >= 0 && xx < w) ? lab[yy * w + xx] : -1;
+  };
+  int slot = -1, l00 = -1;
+  int q3 = 0, q4 = 0;
+  if (y <= h && x <= w) {
+    const int a = L(y - 1, x - 1), b = L(y - 1, x), c = L(y, x - 1);
+    l00 = L(y, x);
+    const int cnt = (a >= 0) + (b >= 0) + (c >= 0) + (l00 >= 0);
+    const int any = max(max(a, b), max(c, l00));          // all non-negative ones are equal
+    if (any >= 0) slot = so[any];
+    q3 = cnt == 3; q4 = cnt == 4;
+  }
+  if (slot >= max_comps) slot = -1;                       // overflow: reported via n_comps > max_comps
+  const unsigned active = __ballot_sync(0xffffffffu, slot >= 0);
+  if (slot < 0) return;
+  const unsigned grp = __match_any_sync(active, slot);
+  const int leader = __ffs(grp) - 1;
+  const int lane = threadIdx.x & 31;
+  const bool own = l00 >= 0;
+  const int sq3 = group_sum(grp, q3), sq4 = group_sum(grp, q4);
+  const int sfill = group_sum(grp, own ? 1 : 0);
+  const int spix = group_sum(grp, (own && mask[(size_t)n * h * w + y * w + x] != 0) ? 1 : 0);
+  const int xmn = __reduce_min_sync(grp, own ? x : 0x7fffffff);
+  const int ymn = __reduce_min_sync(grp, own ? y : 0x7fffffff);
+  const int xmx = __reduce_max_sync(grp, own ? x : -1);
+  const int ymx = __reduce_max_sync(grp, own ? y : -1);
+  if (lane == leader) {
+    CompRec* r = cr + slot;
+    if (sq3) atomicAdd(&r->q3, sq3);
+    if (sq4) atomicAdd(&r->q4, sq4);
+    if (sfill) {
+      atomicAdd(&r->n_filled, sfill);
+      if (spix) atomicAdd(&r->n_pixels, spix);
+      atomicMin(&r->xmin, xmn); atomicMin(&r->ymin, ymn);
+      atomicMax(&r->xmax, xmx); atomicMax(&r->ymax, ymx);
+    }
+  }
+  if (n_cls > 0) {
+    // np_softmax (utils.py:135-138) in float32, accumulated in 2^-24 fixed point so that the sum
+    // does not depend on the order of the atomics (segmap_manager.py:65 takes the mean, argmax).
+    float e[UBD_MAX_CLASSES];
+    float s = 1.f;
+    if (own) {
+      const float* lg = cls_logits + ((size_t)n * h * w + y * w + x) * cls_stride;
+      float mx = lg[0];
+      for (int c = 1; c < n_cls; ++c) mx = fmaxf(mx, lg[c]);
+      s = 0.f;
+      for (int c = 0; c < n_cls; ++c) { e[c] = expf(lg[c] - mx); s += e[c]; }
+    }
+    for (int c = 0; c < n_cls; ++c) {
+      const unsigned fx = own ? (unsigned)(e[c] / s * 16777216.0f) : 0u;
+      const unsigned tot = __reduce_add_sync(grp, fx);
+      if (lane == leader && tot)
+        atomicAdd(&cls_sums[((size_t)n * max_comps + slot) * n_cls + c], (unsigned long long)tot);
+    }
+  }
+}
+
+// Kept components (2*contourArea > min_area_x2, utils.py:55), compacted image-major and, inside an
+// image, in DESCENDING label order (cv2 lists external contours bottom-up).
+struct OutRec {
+  int image, label, xmin, ymin, xmax, ymax, n_pixels, n_filled, area_x2, class_id, slot;
+};
+struct CclTotals { int total_kept, total_pts, max_ncomp, pad; };
+
+__global__ void __launch_bounds__(256)
+ccl_count_kept_kernel(const CompRec* __restrict__ comps, const int* __restrict__ n_comps,
+                      int* __restrict__ kept_count, CclTotals* __restrict__ totals,
+                      int max_comps, int min_area_x2) {
+  const int n = blockIdx.x;
+  const int cnt = min(n_comps[n], max_comps);
+  const CompRec* cr = comps + (size_t)n * max_comps;
+  int k = 0;
+  for (int s = threadIdx.x; s < cnt; s += blockDim.x) k += (2 * cr[s].q4 + cr[s].q3) > min_area_x2;
+  __shared__ int red[8];
+  k = __reduce_add_sync(0xffffffffu, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    kept_count[n] = t;
+    atomicAdd(&totals->total_kept, t);
+    atomicMax(&totals->max_ncomp, n_comps[n]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_compact_kernel(const CompRec* __restrict__ comps, const unsigned long long* __restrict__ cls_sums,
+                   int n_cls, const int* __restrict__ n_comps, const int* __restrict__ kept_count,
+                   OutRec* __restrict__ out, int* __restrict__ out_index_of_slot,
+                   int max_comps, int max_out, int min_area_x2) {
+  const int n = blockIdx.x;
+  const int cnt = min(n_comps[n], max_comps);
+  const CompRec* cr = comps + (size_t)n * max_comps;
+  __shared__ int s_base;
+  __shared__ int warp_cnt[8], warp_off[8], chunk_total;
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int i = 0; i < n; ++i) o += kept_count[i];
+    s_base = o;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const int s = cnt - 1 - i;                       // descending slot = descending label
+    bool keep = false;
+    CompRec r;
+    if (i < cnt) { r = cr[s]; keep = (2 * r.q4 + r.q3) > min_area_x2; }
+    const unsigned bits = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[wid] = __popc(bits);
+    __syncthreads();
+    if (wid == 0) {
+      const int own = lane < nwarps ? warp_cnt[lane] : 0;
+      int v = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      if (lane < nwarps) warp_off[lane] = v - own;
+      if (lane == 31) chunk_total = v;
+    }
+    __syncthreads();
+    if (i < cnt) {
+      int oi = -1;
+      if (keep) {
+        oi = s_base + warp_off[wid] + __popc(bits & ((1u << lane) - 1u));
+        if (oi < max_out) {
+          OutRec o;
+          o.image = n; o.label = r.label; o.xmin = r.xmin; o.ymin = r.ymin; o.xmax = r.xmax; o.ymax = r.ymax;
+          o.n_pixels = r.n_pixels; o.n_filled = r.n_filled; o.area_x2 = 2 * r.q4 + r.q3; o.slot = s;
+          int best = -1;
+          unsigned long long bv = 0ull;
+          for (int c = 0; c < n_cls; ++c) {            // np.argmax: first maximum wins
+            const unsigned long long v = cls_sums[((size_t)n * max_comps + s) * n_cls + c];
+            if (best < 0 || v > bv) { best = c; bv = v; }
+          }
+          o.class_id = best;
+          out[oi] = o;
+        } else {
+          oi = -1;
+        }
+      }
+      out_index_of_slot[(size_t)n * max_comps + s] = oi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += chunk_total;
+    __syncthreads();
+  }
+}
+
+// Run end points of kept components: every convex-hull vertex of a component is the first or last
+// pixel of one of its row runs, so these are all cv2.minAreaRect needs (utils.py:56).
+struct HullPt { int comp; int xy; };     // comp = index into the compacted output; xy = (y << 16) | x
+__global__ void __launch_bounds__(256)
+ccl_points_kernel(const int* __restrict__ labels, const int* __restrict__ slot_of,
+                  const int* __restrict__ out_index_of_slot, HullPt* __restrict__ pts,
+                  CclTotals* __restrict__ totals, int h, int w, int max_comps, int max_pts) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  int comp = -1;
+  if (x < w && y < h) {
+    const int* lab = labels + (size_t)n * h * w;
+    const int l = lab[y * w + x];
+    if (l >= 0) {
+      const bool left_end = x == 0 || lab[y * w + x - 1] != l;
+      const bool right_end = x == w - 1 || lab[y * w + x + 1] != l;
+      if (left_end || right_end) {
+        const int slot = slot_of[(size_t)n * h * w + l];
+        if (slot < max_comps) comp = out_index_of_slot[(size_t)n * max_comps + slot];
+      }
+    }
+  }
+  const bool emit = comp >= 0;
+  const unsigned bits = __ballot_sync(0xffffffffu, emit);
+  if (!bits) return;
+  const int lane = threadIdx.x & 31;
+  const int lead = __ffs(bits) - 1;
+  int base = 0;
+  if (lane == lead) base = atomicAdd(&totals->total_pts, __popc(bits));
+  base = __shfl_sync(0xffffffffu, base, lead);
+  if (emit) {
+    const int idx = base + __popc(bits & ((1u << lane) - 1u));
+    if (idx < max_pts) { HullPt p; p.comp = comp; p.xy = (y << 16) | x; pts[idx] = p; }
+  }
+}

@@ -1,0 +1,57 @@
+// Shared definitions for libubd (sm_100a).  See include/ubd.h for the ABI and DESIGN.md for layouts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ubd.h"
+
+#define UBD_NF 24          // n_filters, net.py:289
+#define UBD_NG 6           // 24 channels = 6 planes of 4 fp32 (one 16-byte unit per pixel and plane)
+#define UBD_NLAYERS_DIL 6  // net.py:298-304
+
+// Feature maps live in HBM as "planar-by-4": act[n][g][y][x] of float4 (channels 4g..4g+3).
+// One pixel of one plane is 16 bytes = one shared-memory core-matrix row of the tcgen05 K-major
+// no-swizzle layout, so a (dy,dx) tap shift is a pure address offset for every kernel.
+__host__ __device__ __forceinline__ size_t act_index(int n, int g, int y, int x, int H, int W) {
+  return ((size_t)(n * UBD_NG + g) * H + y) * W + x;
+}
+
+struct WeightSpec {
+  // offsets (in floats) of the 23 Keras arrays inside the flat parameter buffer (W1 order)
+  int64_t off[UBD_N_WEIGHT_ARRAYS];
+  int64_t size[UBD_N_WEIGHT_ARRAYS];
+  int64_t total;
+  int cin, n_out;
+};
+
+static inline WeightSpec make_weight_spec(int grey, int n_classes) {
+  WeightSpec s;
+  s.cin = grey ? 1 : 3;
+  s.n_out = 1 + n_classes;
+  int k = 0;
+  int64_t o = 0;
+  auto add = [&](int64_t n) { s.off[k] = o; s.size[k] = n; o += n; ++k; };
+  int cins[3] = {s.cin, UBD_NF, UBD_NF};
+  for (int i = 0; i < 3; ++i) { add(9 * cins[i]); add((int64_t)cins[i] * UBD_NF); add(UBD_NF); }
+  for (int i = 0; i < 6; ++i) { add(9 * UBD_NF * UBD_NF); add(UBD_NF); }
+  add((int64_t)UBD_NF * s.n_out); add(s.n_out);
+  s.total = o;
+  return s;
+}
+
+#define UBD_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+      return UBD_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define UBD_FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+static const int kDilations[UBD_NLAYERS_DIL] = {1, 2, 4, 8, 16, 1};
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }

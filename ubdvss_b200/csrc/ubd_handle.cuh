@@ -1,0 +1,51 @@
+// The handle behind ubd_handle: one device, one stream, lazily sized workspaces.
+#pragma once
+#include <utility>
+#include "ubd_common.cuh"
+
+struct DevBuf { void* p = nullptr; size_t cap = 0; };
+
+struct ubd_handle_s {
+  int device = 0;
+  bool grey = true, fml = true;
+  int n_classes = 0;
+  int precision = UBD_FP32;
+  int n_sm = 148;
+  WeightSpec spec;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // optional CUDA-event profiling of kernel groups (option "profile")
+  bool profile = false;
+  struct Prof { double ms = 0; int64_t launches = 0; };
+  Prof prof_dil, prof_stem, prof_ccl, prof_head;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<Prof*, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  std::string err;
+  int64_t launches = 0;
+
+  float* d_params = nullptr;      // flat parameter buffer, Keras get_weights() order and layout
+  float* d_lut = nullptr;         // uint8 -> mobilenet_like preprocessing table
+  bool have_weights = false;
+  bool tc_weights_dirty = true;   // tensor-core weight images must be rebuilt from d_params
+
+  int opt_chunk = 0;              // images per L2-resident chunk (0 = auto)
+  int opt_max_comps = 4096;       // component slots per image
+  int opt_max_points = 0;         // hull candidate capacity (0 = auto)
+
+  // inference workspaces
+  DevBuf d_images, d_logits, d_mask;
+  DevBuf act1, act2, mapA, mapB;
+  DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
+  DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
+  // training workspaces
+  DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss;
+  int64_t adam_t = 0;
+  bool have_grads = false;
+  void* h_stage = nullptr;        // pinned staging (unused unless requested)
+
+  std::vector<DevBuf*> all_bufs() {
+    return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &parent, &labels, &slot_of, &comps,
+            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &t_acts, &t_grads_act,
+            &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
+  }
+};
