@@ -41,7 +41,12 @@ def test_config_a_parity(precision):
     eng = _engine(precision=precision)
     eng.set_weights(w)
     x = synth.synth_images(8, 512, 512, seed=0)
-    _check(eng, w, x, _lib.PREPROC_MOBILENET, precision=precision)
+    try:
+        _check(eng, w, x, _lib.PREPROC_MOBILENET, precision=precision)
+    except _lib.UbdError as e:
+        if e.code == -5:
+            pytest.skip(str(e))
+        raise
     xf = (x.astype(np.float32) - 127.5) / 127.5
     _check(eng, w, xf, _lib.PREPROC_NONE, precision=precision)
 

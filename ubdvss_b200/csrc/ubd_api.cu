@@ -197,7 +197,7 @@ extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const i
   int rc = check_weight_args(h, arrays, n_elems, n_arrays);
   if (rc) return rc;
   UBD_CUDA(cudaSetDevice(h->device));
-  std::vector<float> flat(h->spec.total);
+  std::vector<float> flat(h->spec.total, 0.f);
   for (int i = 0; i < n_arrays; ++i) {
     if (!arrays[i]) UBD_FAIL(UBD_ERR_ARG, "weights: NULL array");
     memcpy(flat.data() + h->spec.off[i], arrays[i], h->spec.size[i] * sizeof(float));

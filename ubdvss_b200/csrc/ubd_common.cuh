@@ -32,7 +32,8 @@ static inline WeightSpec make_weight_spec(int grey, int n_classes) {
   s.n_out = 1 + n_classes;
   int k = 0;
   int64_t o = 0;
-  auto add = [&](int64_t n) { s.off[k] = o; s.size[k] = n; o += n; ++k; };
+  // every array starts on a 128-byte boundary (vector loads / bulk copies); the gaps stay zero
+  auto add = [&](int64_t n) { s.off[k] = o; s.size[k] = n; o += (n + 31) & ~(int64_t)31; ++k; };
   int cins[3] = {s.cin, UBD_NF, UBD_NF};
   for (int i = 0; i < 3; ++i) { add(9 * cins[i]); add((int64_t)cins[i] * UBD_NF); add(UBD_NF); }
   for (int i = 0; i < 6; ++i) { add(9 * UBD_NF * UBD_NF); add(UBD_NF); }
