@@ -151,6 +151,11 @@ int ubd_get_stat(ubd_handle h, const char* name, double* value);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t ubd_launch_count(ubd_handle h);
 
+/* Test hook (layer-level parity, bring-up): dilated layer `layer` (0..5 = conv2d_1..6 with its own
+ * weights and dilation) on a host NHWC (n,mh,mw,24) map through the FP32 or the tcgen05 kernel. */
+int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float* out_nhwc, int layer,
+                            int n, int mh, int mw, int precision);
+
 #ifdef __cplusplus
 }
 #endif

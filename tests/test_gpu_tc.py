@@ -1,0 +1,54 @@
+"""-m gpu: the tcgen05 (kind::tf32) implicit-GEMM kernel vs the FP32 CUDA-core kernel and the
+oracle, layer by layer (every dilation, ragged sizes) -- the bring-up and regression test of the
+shared-memory descriptor / phase-decomposition logic."""
+import numpy as np
+import pytest
+
+from oracle import net as onet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ubdvss_b200.engine import Engine
+    e = Engine()
+    e.set_weights(onet.init_weights(0, seed=1234))
+    return e
+
+
+def _ref_layer(w, x, layer, tf32):
+    k, b = w[9 + 2 * layer], w[10 + 2 * layer]
+    if tf32:
+        k = onet.round_tf32(k); x = onet.round_tf32(x)
+    y = onet._conv3x3_np(x.astype(np.float64), k.astype(np.float64), onet.DILATIONS[layer]) + b
+    return np.maximum(y, 0)
+
+
+@pytest.mark.parametrize("layer", range(6))
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 32, 256), (3, 20, 36), (1, 136, 240), (1, 4, 4)])
+def test_tf32_layer_matches_fp32_and_oracle(eng, layer, shape):
+    rng = np.random.default_rng(layer * 10 + shape[1])
+    x = np.maximum(rng.normal(0, 1, size=shape + (24,)), 0).astype(np.float32)     # post-ReLU-like input
+    w = onet.init_weights(0, seed=1234)
+    got32 = eng.debug_dilated_layer(x, layer, "fp32")
+    ref = _ref_layer(w, x, layer, tf32=False)
+    assert np.abs(got32 - ref).max() <= 1e-4
+    got = eng.debug_dilated_layer(x, layer, "tf32")
+    ref_t = _ref_layer(w, x, layer, tf32=True)
+    # against the tf32-rounded oracle only fp32 accumulation order remains
+    assert np.abs(got - ref_t).max() <= 2e-4, np.abs(got - ref_t).max()
+    assert np.abs(got - ref).max() <= 2e-2
+
+
+def test_tf32_delta_taps(eng):
+    """A delta input pins every tap's (dy,dx) address offset at every dilation."""
+    w = onet.init_weights(0, seed=1234)
+    for layer in range(6):
+        d = onet.DILATIONS[layer]
+        x = np.zeros((1, 64, 160, 24), np.float32)
+        x[0, 32, 70, 5] = 1.0
+        x[0, 3, 150, 17] = 2.0
+        got = eng.debug_dilated_layer(x, layer, "tf32")
+        ref = _ref_layer(w, x, layer, tf32=True)
+        assert np.abs(got - ref).max() <= 1e-5, (layer, d)

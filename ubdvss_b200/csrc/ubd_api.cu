@@ -278,7 +278,10 @@ static int run_stem(ubd_handle h, const void* d_img, int in_dtype, int preproc, 
   if (rc) return rc;
   rc = launch_sep<24, 1, false, float>(h, (const float*)act1, act2, 1, n, H2, W2, H2, W2, 1, 1, nullptr, 0.f, 0.f);
   if (rc) return rc;
-  rc = launch_sep<24, 2, false, float>(h, (const float*)act2, act3, 2, n, H2, W2, H4, W4, p2, p2, nullptr, 0.f, 0.f);
+  // the tensor-core layers read tf32: round (rna) where the map is produced instead of letting the
+  // MMA truncate it
+  rc = launch_sep<24, 2, false, float>(h, (const float*)act2, act3, 2, n, H2, W2, H4, W4, p2, p2, nullptr,
+                                       h->precision == UBD_TF32 ? -1.f : 0.f, 0.f);
   return rc;
 }
 
@@ -304,11 +307,12 @@ static int launch_head(ubd_handle h, const float4* in, float* logits, uint8_t* m
 
 static int pick_chunk(ubd_handle h, int n, int H, int W) {
   if (h->opt_chunk > 0) return std::min(n, h->opt_chunk);
-  // keep the two ping-pong quarter-resolution maps (+ the stem's half-resolution maps) of one chunk
-  // inside the ~126 MB L2: 2 * 96 B/px at H/4 + 2 * 96 B/px at H/2 per image
-  const double per_img = (double)H * W * (2.0 * 96 / 16 + 2.0 * 96 / 4);
-  int c = (int)(96e6 / per_img);
-  return std::max(1, std::min(n, c));
+  // Images per sweep through the layer stack.  Two opposing needs: enough work items per launch to
+  // fill 148 SMs evenly, and the two ping-pong quarter-resolution maps (2 * 96 B per map pixel per
+  // image) small enough to stay resident in the 126 MB L2 between layers.
+  const double per_img = (double)(H / 4) * (W / 4) * 2.0 * 96.0;
+  int c = (int)(100e6 / per_img);
+  return std::max(1, std::min(n, std::min(c, 16)));
 }
 
 // d_img: device images.  d_logits (nullable) / d_mask (nullable): device outputs for the whole batch.
@@ -335,7 +339,7 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
       const float* w = h->d_params + h->spec.off[9 + 2 * l];
       const float* b = h->d_params + h->spec.off[10 + 2 * l];
       if (h->precision == UBD_FP32) rc = launch_dil_fp32(h, A, B, w, b, nullptr, cn, h4, w4, kDilations[l], 0);
-      else rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l]);
+      else rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*round_out=*/l < UBD_NLAYERS_DIL - 1);
       if (rc) return rc;
       std::swap(A, B);
     }
@@ -466,7 +470,7 @@ extern "C" int ubd_forward(ubd_handle h, const void* images, int in_dtype, int n
   if (rc) return rc;
   UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, lb, cudaMemcpyDeviceToHost, h->stream));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
-  return UBD_OK;
+  return h->precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
 }
 
 static int segment_common(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
@@ -475,8 +479,10 @@ static int segment_common(ubd_handle h, const void* d_img, int in_dtype, int n, 
   const int n_cls = h->n_classes;
   int rc = forward_device(h, d_img, in_dtype, n, H, W, preproc, d_logits, d_mask, logit_thr);
   if (rc) return rc;
-  return ccl_device(h, d_mask, n_cls ? d_logits + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4, min_area_x2,
+  rc = ccl_device(h, d_mask, n_cls ? d_logits + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4, min_area_x2,
                     labels_out_host, comps_out, max_comps, n_comps_per_image);
+  if (rc) return rc;
+  return h->precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
 }
 
 extern "C" int ubd_segment_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int H, int W, int preproc,
@@ -514,8 +520,10 @@ extern "C" int ubd_segment(ubd_handle h, const void* images, int in_dtype, int n
   if (mask_out) UBD_CUDA(cudaMemcpyAsync(mask_out, h->d_mask.p, q, cudaMemcpyDeviceToHost, h->stream));
   if (logits_out) UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, q * h->spec.n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   const int n_cls = h->n_classes;
-  return ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4,
-                    min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
+  rc = ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4,
+                  min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
+  if (rc) return rc;
+  return h->precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
 }
 
 extern "C" int ubd_postprocess(ubd_handle h, const uint8_t* mask, const float* cls_logits, int n, int mh, int mw,
@@ -535,6 +543,62 @@ extern "C" int ubd_postprocess(ubd_handle h, const uint8_t* mask, const float* c
   }
   return ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p : nullptr, n_cls, n_cls, n, mh, mw,
                     min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
+}
+
+// Test hook: one dilated layer (0..5, its own weights and dilation) on an NHWC 24-channel host map,
+// through the FP32 kernel or the tcgen05 kernel, for layer-level parity tests and bring-up.
+__global__ void nhwc_to_planar_kernel(const float* __restrict__ src, float4* __restrict__ dst, int n, int hh, int ww) {
+  const size_t npx = (size_t)hh * ww;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * npx) return;
+  const size_t img = i / npx, p = i % npx;
+  for (int g = 0; g < UBD_NG; ++g) {
+    const float* s = src + i * UBD_NF + 4 * g;
+    dst[(img * UBD_NG + g) * npx + p] = make_float4(s[0], s[1], s[2], s[3]);
+  }
+}
+__global__ void planar_to_nhwc_kernel(const float4* __restrict__ src, float* __restrict__ dst, int n, int hh, int ww) {
+  const size_t npx = (size_t)hh * ww;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * npx) return;
+  const size_t img = i / npx, p = i % npx;
+  for (int g = 0; g < UBD_NG; ++g) {
+    const float4 v = src[(img * UBD_NG + g) * npx + p];
+    float* d = dst + i * UBD_NF + 4 * g;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+}
+
+extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float* out_nhwc, int layer,
+                                       int n, int mh, int mw, int precision) {
+  if (!h) return UBD_ERR_ARG;
+  if (!in_nhwc || !out_nhwc || layer < 0 || layer >= UBD_NLAYERS_DIL || n < 1 || mh < 1 || mw < 1)
+    UBD_FAIL(UBD_ERR_ARG, "bad argument");
+  if (!h->have_weights) UBD_FAIL(UBD_ERR_NO_WEIGHTS, "no weights loaded");
+  UBD_CUDA(cudaSetDevice(h->device));
+  const size_t elems = (size_t)n * mh * mw * UBD_NF;
+  ENSURE(h->t_scratch, elems * sizeof(float));
+  ENSURE(h->mapA, elems * sizeof(float));
+  ENSURE(h->mapB, elems * sizeof(float));
+  UBD_CUDA(cudaMemcpyAsync(h->t_scratch.p, in_nhwc, elems * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  const unsigned blocks = (unsigned)(((size_t)n * mh * mw + 255) / 256);
+  nhwc_to_planar_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->t_scratch.p, (float4*)h->mapA.p, n, mh, mw); LAUNCH_CHECK();
+  const float* w = h->d_params + h->spec.off[9 + 2 * layer];
+  const float* b = h->d_params + h->spec.off[10 + 2 * layer];
+  int rc;
+  if (precision == UBD_FP32) {
+    rc = launch_dil_fp32(h, (float4*)h->mapA.p, (float4*)h->mapB.p, w, b, nullptr, n, mh, mw, kDilations[layer], 0);
+  } else {
+    const int saved = h->precision;
+    h->precision = precision;
+    rc = tc_launch_dilconv(h, (float4*)h->mapA.p, (float4*)h->mapB.p, layer, n, mh, mw, kDilations[layer], 0);
+    h->precision = saved;
+  }
+  if (rc) return rc;
+  planar_to_nhwc_kernel<<<blocks, 256, 0, h->stream>>>((const float4*)h->mapB.p, (float*)h->t_scratch.p, n, mh, mw); LAUNCH_CHECK();
+  UBD_CUDA(cudaMemcpyAsync(out_nhwc, h->t_scratch.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  return precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
 }
 
 #include "ubd_train_api.inc"

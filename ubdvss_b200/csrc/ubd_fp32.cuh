@@ -11,6 +11,12 @@
 //   pad_t / pad_l: zero rows/cols before the image (1,1 for the FML stride-2 layers net.py:229-232
 //         and for 'same' stride 1; 0,0 for TF 'same' stride 2 on even sizes).
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 template <int CIN, int STRIDE, bool RAW, typename TIn>
 __global__ void __launch_bounds__(128)
 sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
@@ -87,6 +93,9 @@ sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
       a.z = fmaf(d[c], w.z, a.z); a.w = fmaf(d[c], w.w, a.w);
     }
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+    if (!RAW && pre_scale < 0.f) {     // producer-side rounding to the tf32 grid for the tensor-core layers
+      a.x = rna_tf32(a.x); a.y = rna_tf32(a.y); a.z = rna_tf32(a.z); a.w = rna_tf32(a.w);
+    }
     out[act_index(n, og, y, x, Ho, Wo)] = a;
   }
 }

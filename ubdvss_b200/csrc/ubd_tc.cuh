@@ -1,9 +1,380 @@
-// tcgen05 implicit-GEMM path for the dilated layers (filled in by ubd_tc_impl).
+// tcgen05 implicit-GEMM path for the dilated 3x3 24->24 layers (net.py:298-304), sm_100a only.
+//
+// GEMM view of one output row segment:  D[128 px, 32 oc] += A[128 px, K] * B[K, 32 oc],
+//   K = 9 taps x 24 channels; kind::tf32 consumes K = 8 per instruction -> 27 MMAs per segment.
+//
+// Operand A is the input feature map itself.  Maps are "planar-by-4" in HBM (act[n][g][y][x] float4),
+// so one pixel of one plane is 16 bytes = one row of a UMMA core matrix (8 rows x 16 B) of the
+// K-major SWIZZLE_NONE canonical layout ((8,m),2):((16 B, SBO),LBO).  A row slot in shared memory
+// is [6 planes][160 px][16 B]; 8 consecutive pixels form a core matrix (SBO = 128 B), the two K
+// cores of one MMA are two adjacent channel planes (LBO = plane stride).  A (dy,dx) tap is then
+// nothing but a different descriptor start address: slot(row + dy) + (16 + dx*d) * 16 B.
+// No im2col copy exists anywhere.
+//
+// Dilation is handled by phase decomposition in y: the rows r, r+d, r+2d, ... of an image form an
+// independent 1-dilated problem, so a CTA walks a phase top to bottom with a ring of row slots:
+// each input row is fetched once (+2 halo rows per item) and used by three output rows.  Rows are
+// staged by the TMA unit with cp.async.bulk (one contiguous 16*(128+2d)-byte run per plane, image
+// borders filled from a zero page), completion on mbarriers.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over a static item list):
+//   warp 0   : producer  - bulk copies into the slot ring      (empty[] -> full[])
+//   warp 1   : MMA issue - one elected lane, 27 tcgen05.mma per segment into a TMEM accumulator,
+//              tcgen05.commit to tmem_full[] and to the empty[] of the row that is no longer needed
+//   warps 2-5: epilogue  - tcgen05.ld (lane = pixel, 24 columns = channels), bias + ReLU,
+//              six coalesced float4 stores (one per plane)
 #pragma once
 #include "ubd_handle.cuh"
-static void tc_setup_attributes() {}
-static int tc_launch_dilconv(ubd_handle h, const float4* in, float4* out, int layer, int n, int hh, int ww, int d) {
-  (void)in; (void)out; (void)layer; (void)n; (void)hh; (void)ww; (void)d;
-  h->err = "tensor-core path not built in this revision";
-  return UBD_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int TW = 128;                       // pixels per segment = UMMA M
+constexpr int HALO = 16;                      // largest dilation
+constexpr int BW = TW + 2 * HALO;             // pixels per plane in a slot
+constexpr int PLANE_BYTES = BW * 16;          // 2560
+constexpr int SLOT_BYTES = UBD_NG * PLANE_BYTES;   // 15360
+constexpr int NS = 8;                         // row slots in the ring
+constexpr int NACC = 4;                       // TMEM accumulator stages
+constexpr int UMMA_N = 32;                    // 24 output channels padded to a legal N for M=128
+constexpr int TMEM_COLS = NACC * UMMA_N;      // 128
+constexpr int N_MMA = 27;                     // 9 taps x 3 K-pairs (8 tf32 each)
+constexpr int B_TILE_BYTES = UMMA_N * 8 * 4;  // 1024: [2 K cores][4 oc groups][8 rows][16 B]
+constexpr int W_BYTES = N_MMA * B_TILE_BYTES; // 27648
+constexpr int WB_BYTES = W_BYTES + 128;       // + bias[24] padded to 32 floats
+constexpr int RQ = 8;                         // output rows per work item
+constexpr int THREADS = 192;
+constexpr int ZERO_BYTES = PLANE_BYTES;
+
+struct Smem {
+  uint8_t slots[NS * SLOT_BYTES];
+  uint8_t wimg[W_BYTES];
+  float bias[32];
+  uint64_t full[NS], empty[NS], tfull[NACC], tempty[NACC], wbar;
+  uint32_t tmem_base;
+  int abort_flag;
+};
+constexpr size_t SMEM_BYTES = sizeof(Smem) + 128;    // + manual 128 B alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a wrong descriptor / byte count must end in an error code, never in a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+    if (*abort_flag) return false;
+    if (clock64() - t0 > 1500000000LL) { atomicCAS(gerr, 0, code); *abort_flag = 1; return false; }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 32 (cute::UMMA::InstrDescriptor).
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((UMMA_N >> 3) << 17) | ((TW >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_TF32), "r"(accumulate), "r"(0u) : "memory");
+}
+
+struct Item { int n, x0, r, q0, rows, nq; };
+
+struct Sched {
+  int n_imgs, h, w, d, n_strips, n_chunks, total;
+  __device__ Sched(int n_imgs_, int h_, int w_, int d_) : n_imgs(n_imgs_), h(h_), w(w_), d(d_) {
+    n_strips = (w + TW - 1) / TW;
+    n_chunks = ((h + d - 1) / d + RQ - 1) / RQ;
+    total = n_imgs * n_strips * d * n_chunks;
+  }
+  __device__ bool get(int idx, Item& it) const {
+    const int c = idx % n_chunks; int t = idx / n_chunks;
+    it.r = t % d; t /= d;
+    it.x0 = (t % n_strips) * TW;
+    it.n = t / n_strips;
+    it.nq = it.r < h ? (h - it.r + d - 1) / d : 0;
+    it.q0 = c * RQ;
+    it.rows = min(RQ, it.nq - it.q0);
+    return it.rows > 0;
+  }
+};
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+// in/out: planar-by-4 maps of n_imgs images; wb: this layer's B image (W_BYTES) followed by bias[32].
+__global__ void __launch_bounds__(THREADS, 1)
+dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, const uint8_t* __restrict__ wb,
+                    const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int round_out, int* gerr) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  volatile int* abort_flag = &S.abort_flag;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&S.tfull[i]), 1); mbar_init(smem_u32(&S.tempty[i]), 4); }
+    mbar_init(smem_u32(&S.wbar), 1);
+    S.abort_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_base;
+  const Sched sched(n_imgs, h, w, d);
+  const uint32_t slots0 = smem_u32(S.slots);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer (one lane)
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&S.wbar), WB_BYTES);
+      bulk_g2s(smem_u32(S.wimg), wb, WB_BYTES, smem_u32(&S.wbar));
+      const uint32_t row_px = TW + 2 * d;
+      const uint32_t row_bytes = UBD_NG * row_px * 16;
+      uint32_t lseq = 0;
+      bool ok = true;
+      for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+        Item it;
+        if (!sched.get(idx, it)) continue;
+        const int xl = it.x0 - d, xr = it.x0 + TW + d;
+        const int cl = max(xl, 0), cr = min(xr, w);
+        const uint32_t nleft = cl - xl, ndata = cr - cl, nright = xr - cr;
+        for (int q = it.q0 - 1; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
+          const uint32_t slot = lseq % NS;
+          ok = mbar_wait(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 1);
+          if (!ok) break;
+          const uint32_t bar = smem_u32(&S.full[slot]);
+          mbar_expect_tx(bar, row_bytes);
+          const uint32_t dst0 = slots0 + slot * SLOT_BYTES + (HALO - d) * 16;
+          if (q < 0 || q >= it.nq) {
+#pragma unroll
+            for (int g = 0; g < UBD_NG; ++g) bulk_g2s(dst0 + g * PLANE_BYTES, zeros, row_px * 16, bar);
+          } else {
+            const int y = it.r + q * d;
+#pragma unroll
+            for (int g = 0; g < UBD_NG; ++g) {
+              const uint32_t dst = dst0 + g * PLANE_BYTES;
+              if (nleft) bulk_g2s(dst, zeros, nleft * 16, bar);
+              bulk_g2s(dst + nleft * 16, in + act_index(it.n, g, y, cl, h, w), ndata * 16, bar);
+              if (nright) bulk_g2s(dst + (nleft + ndata) * 16, zeros, nright * 16, bar);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 2);
+      const uint32_t wsm = smem_u32(S.wimg);
+      uint32_t lbase = 0, oseq = 0, waited = 0;      // waited = number of row loads known to have landed
+      for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+        Item it;
+        if (!sched.get(idx, it)) continue;
+        for (int j = 0; j < it.rows && ok; ++j, ++oseq) {
+          while (waited < lbase + j + 3 && ok) {
+            ok = mbar_wait(smem_u32(&S.full[waited % NS]), (waited / NS) & 1, abort_flag, gerr, 3);
+            ++waited;
+          }
+          if (!ok) break;
+          const uint32_t acc = oseq % NACC;
+          ok = mbar_wait(smem_u32(&S.tempty[acc]), ((oseq / NACC) & 1) ^ 1, abort_flag, gerr, 4);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * UMMA_N;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const uint32_t slot = (lbase + j + 1 + dy) % NS;
+            const uint32_t a_addr = slots0 + slot * SLOT_BYTES + (HALO + dx * d) * 16;
+#pragma unroll
+            for (int kp = 0; kp < 3; ++kp) {
+              const uint64_t adesc = make_desc(a_addr + kp * 2 * PLANE_BYTES, PLANE_BYTES, 128);
+              const uint64_t bdesc = make_desc(wsm + (tap * 3 + kp) * B_TILE_BYTES, 512, 128);
+              umma_tf32(tmem_d, adesc, bdesc, (tap | kp) != 0);
+            }
+          }
+          umma_commit(smem_u32(&S.tfull[acc]));
+          umma_commit(smem_u32(&S.empty[(lbase + j) % NS]));           // top row of this window is done
+          if (j == it.rows - 1) {
+            umma_commit(smem_u32(&S.empty[(lbase + j + 1) % NS]));
+            umma_commit(smem_u32(&S.empty[(lbase + j + 2) % NS]));
+          }
+        }
+        lbase += it.rows + 2;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int quad = warp & 3;                              // TMEM lane quadrant this warp may read
+    bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 5);
+    float bias[UBD_NF];
+#pragma unroll
+    for (int c = 0; c < UBD_NF; ++c) bias[c] = ok ? S.bias[c] : 0.f;
+    uint32_t oseq = 0;
+    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+      Item it;
+      if (!sched.get(idx, it)) continue;
+      const int x = it.x0 + quad * 32 + lane;
+      for (int j = 0; j < it.rows && ok; ++j, ++oseq) {
+        const uint32_t acc = oseq % NACC;
+        ok = mbar_wait(smem_u32(&S.tfull[acc]), (oseq / NACC) & 1, abort_flag, gerr, 6);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UMMA_N;
+        uint32_t v[24];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
+                     : "r"(taddr + 16));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&S.tempty[acc]));
+        const int y = it.r + (it.q0 + j) * d;
+        if (x < w) {
+#pragma unroll
+          for (int g = 0; g < UBD_NG; ++g) {
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v[4 * g + 0]) + bias[4 * g + 0], 0.f);
+            o.y = fmaxf(__uint_as_float(v[4 * g + 1]) + bias[4 * g + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(v[4 * g + 2]) + bias[4 * g + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(v[4 * g + 3]) + bias[4 * g + 3], 0.f);
+            if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            out[act_index(it.n, g, y, x, h, w)] = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// Builds, for the 6 dilated layers, the UMMA B images from the Keras HWIO kernels in the flat
+// parameter buffer: per (tap, K-pair) a [32 oc x 8 ic] K-major tile, values rounded to tf32 (rna),
+// output channels 24..31 zero; followed by the bias.
+__global__ void build_wimg_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
+                                  const int64_t* __restrict__ boff, uint8_t* __restrict__ wimg_all) {
+  const int layer = blockIdx.x;
+  const float* K = params + koff[layer];
+  const float* B = params + boff[layer];
+  float* dst = reinterpret_cast<float*>(wimg_all + (size_t)layer * WB_BYTES);
+  for (int i = threadIdx.x; i < W_BYTES / 4; i += blockDim.x) {
+    const int t = i / 256, rem = i % 256;              // t = tap*3 + kp
+    const int kcore = rem / 128, ngroup = (rem % 128) / 32, row = (rem % 32) / 4, col = rem % 4;
+    const int tap = t / 3, kp = t % 3;
+    const int ic = kp * 8 + kcore * 4 + col, oc = ngroup * 8 + row;
+    dst[i] = oc < UBD_NF ? round_tf32(K[(tap * UBD_NF + ic) * UBD_NF + oc]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[W_BYTES / 4 + i] = i < UBD_NF ? B[i] : 0.f;
+}
+
+}  // namespace tc
+
+static void tc_setup_attributes() {
+  cudaFuncSetAttribute(tc::dilconv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+}
+
+// tc_weights buffer: [6 layers x WB_BYTES][zero page][int err flag][offsets]
+static int tc_prepare(ubd_handle h) {
+  const size_t img = (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
+  const size_t total = img + tc::ZERO_BYTES + 256;
+  if (!h->tc_weights.p) {
+    UBD_CUDA(cudaMalloc(&h->tc_weights.p, total));
+    h->tc_weights.cap = total;
+    UBD_CUDA(cudaMemsetAsync(h->tc_weights.p, 0, total, h->stream));
+    h->tc_weights_dirty = true;
+  }
+  if (h->tc_weights_dirty) {
+    int64_t offs[12];
+    for (int l = 0; l < 6; ++l) { offs[l] = h->spec.off[9 + 2 * l]; offs[6 + l] = h->spec.off[10 + 2 * l]; }
+    int64_t* d_offs = reinterpret_cast<int64_t*>((uint8_t*)h->tc_weights.p + img + tc::ZERO_BYTES + 64);
+    UBD_CUDA(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, h->stream));
+    UBD_CUDA(cudaStreamSynchronize(h->stream));      // offs is a stack array
+    tc::build_wimg_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p);
+    ++h->launches;
+    UBD_CUDA(cudaGetLastError());
+    h->tc_weights_dirty = false;
+  }
+  return UBD_OK;
+}
+
+static inline int* tc_err_flag(ubd_handle h) {
+  return reinterpret_cast<int*>((uint8_t*)h->tc_weights.p + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES + tc::ZERO_BYTES);
+}
+
+static int tc_launch_dilconv(ubd_handle h, const float4* in, float4* out, int layer, int n, int hh, int ww, int d,
+                             int round_out) {
+  if (h->precision != UBD_TF32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path: only tf32 is built in this revision");
+  int rc = tc_prepare(h);
+  if (rc) return rc;
+  const uint8_t* base = (const uint8_t*)h->tc_weights.p;
+  const uint8_t* wb = base + (size_t)layer * tc::WB_BYTES;
+  const uint8_t* zeros = base + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
+  const int n_strips = (ww + tc::TW - 1) / tc::TW;
+  const int n_chunks = ((hh + d - 1) / d + tc::RQ - 1) / tc::RQ;
+  const long long items = (long long)n * n_strips * d * n_chunks;
+  const int grid = (int)std::min<long long>(items, h->n_sm);
+  tc::dilconv_tf32_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>(in, out, wb, zeros, n, hh, ww, d, round_out, tc_err_flag(h));
+  ++h->launches;
+  UBD_CUDA(cudaGetLastError());
+  return UBD_OK;
+}
+
+// Reads (and clears) the device-side barrier-timeout flag; call after a stream synchronize.
+static int tc_check_error(ubd_handle h) {
+  if (!h->tc_weights.p) return UBD_OK;
+  int code = 0;
+  UBD_CUDA(cudaMemcpyAsync(&code, tc_err_flag(h), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  if (code) {
+    cudaMemsetAsync(tc_err_flag(h), 0, sizeof(int), h->stream);
+    UBD_FAIL(UBD_ERR_CUDA, "tcgen05 pipeline barrier timed out (role code " + std::to_string(code) + ")");
+  }
+  return UBD_OK;
 }

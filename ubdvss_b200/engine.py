@@ -189,6 +189,14 @@ class Engine:
     def synchronize(self):
         check(self._h, self._lib.ubd_synchronize(self._h))
 
+    def debug_dilated_layer(self, x_nhwc, layer: int, precision: str = "fp32"):
+        x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
+        n, mh, mw, c = x.shape
+        assert c == 24
+        out = np.empty_like(x)
+        check(self._h, self._lib.ubd_debug_dilated_layer(self._h, ptr(x), ptr(out), layer, n, mh, mw, _lib.PRECISIONS[precision]))
+        return out
+
     def set_stream(self, cuda_stream: int | None):
         check(self._h, self._lib.ubd_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
