@@ -168,6 +168,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     eng = Engine(device=local_rank, precision=args.precision)
     eng.set_weights(weights)
+    if os.environ.get("UBD_CHUNK"):
+        eng.set_option("chunk", int(os.environ["UBD_CHUNK"]))
     B, S = args.batch, args.size
     imgs = make_images(B, S, seed=1 + rank)
     pinned = torch.from_numpy(imgs).pin_memory()
@@ -206,6 +208,7 @@ def main():
     launches = eng.launch_count() - l0
     dil_ms, dil_n = eng.stat("dilconv_ms"), eng.stat("dilconv_launches")
     stem_ms, ccl_ms, head_ms = eng.stat("stem_ms"), eng.stat("ccl_ms"), eng.stat("head_ms")
+    host_ms = [eng.stat(f"host_ms{i}") / args.steps for i in range(5)]
     eng.set_option("profile", 0)
 
     # end to end through the host-buffer ABI call (what ModelRunner.predict does)
@@ -255,7 +258,8 @@ def main():
                 "share_of_step": dil_ms / ms if ms else None,
                 "hbm_frac_whole_step": ALGO_BYTES_PER_IMAGE_1024 * (S * S / 1048576.0) * (value / world) / (pk["hbm_gbs"] * 1e9),
                 "stage_ms_per_step": {"stem": stem_ms / args.steps, "dilated": dil_ms / args.steps,
-                                      "head": head_ms / args.steps, "ccl": ccl_ms / args.steps}}
+                                      "head": head_ms / args.steps, "ccl": ccl_ms / args.steps},
+                "host_ms_per_step": dict(zip(["enqueue_forward", "enqueue_cc", "sync_counts", "sync_records", "boxes"], host_ms))}
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],

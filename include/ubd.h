@@ -156,6 +156,10 @@ int64_t ubd_launch_count(ubd_handle h);
 int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float* out_nhwc, int layer,
                             int n, int mh, int mw, int precision);
 
+/* Tuning hook: with option "tc_trace" = 1 the tcgen05 kernel records cycle stamps of CTA 0
+ * ([3 roles][1024 events][4 stamps], int64); this reads and clears them. */
+int ubd_debug_read_trace(ubd_handle h, long long* out, int n_values);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ubd_grad_buffer": (_i, [_vp, _pp, _pi64]),
     "ubd_adam_step": (_i, [_vp, _f, _f, _f, _f, _f]),
     "ubd_debug_dilated_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),
+    "ubd_debug_read_trace": (_i, [_vp, _vp, _i]),
     "ubd_synchronize": (_i, [_vp]),
     "ubd_set_stream": (_i, [_vp, _vp]),
     "ubd_get_stat": (_i, [_vp, C.c_char_p, C.POINTER(C.c_double)]),

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,14 @@ static void resolve_profile(ubd_handle h) {
   }
   h->pending.clear();
 }
+
+struct HostTimer {
+  ubd_handle h; int slot; std::chrono::steady_clock::time_point t0;
+  HostTimer(ubd_handle h_, int slot_) : h(h_), slot(slot_), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() {
+    if (h->profile) h->host_ms[slot] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
 
 static int ensure(ubd_handle h, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return UBD_OK;
@@ -163,6 +172,7 @@ extern "C" int ubd_get_stat(ubd_handle h, const char* name, double* value) {
   else if (!strcmp(name, "head_ms")) *value = h->prof_head.ms;
   else if (!strcmp(name, "ccl_ms")) *value = h->prof_ccl.ms;
   else if (!strcmp(name, "ccl_launches")) *value = (double)h->prof_ccl.launches;
+  else if (!strncmp(name, "host_ms", 7) && name[7] >= '0' && name[7] <= '7') *value = h->host_ms[name[7] - '0'];
   else UBD_FAIL(UBD_ERR_ARG, std::string("unknown stat ") + name);
   return UBD_OK;
 }
@@ -176,6 +186,11 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
     resolve_profile(h);
     h->profile = value != 0;
     h->prof_dil = h->prof_stem = h->prof_ccl = h->prof_head = ubd_handle_s::Prof();
+    for (double& v : h->host_ms) v = 0;
+  }
+  else if (!strcmp(name, "tc_trace")) {
+    if (value) { ENSURE(h->tc_trace, 3 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
+    else if (h->tc_trace.p) { cudaFree(h->tc_trace.p); h->tc_trace.p = nullptr; h->tc_trace.cap = 0; }
   }
   else if (!strcmp(name, "precision")) { if (value < UBD_FP32 || value > UBD_BF16) UBD_FAIL(UBD_ERR_ARG, "bad precision"); h->precision = (int)value; }
   else UBD_FAIL(UBD_ERR_ARG, std::string("unknown option ") + name);
@@ -243,14 +258,15 @@ static size_t image_bytes(ubd_handle h, int in_dtype, int n, int H, int W) {
 // Separable layer launcher (L1: raw image; L2/L3: planar maps).
 template <int CIN, int STRIDE, bool RAW, typename TIn>
 static int launch_sep(ubd_handle h, const TIn* in, float4* out, int layer, int n, int H, int W, int Ho, int Wo,
-                      int pad_t, int pad_l, const float* lut, float pre_scale, float pre_shift) {
+                      int pad_t, int pad_l, const float* lut, float pre_scale, float pre_shift,
+                      int in_mpad = 0, int out_mpad = 0) {
   const float* base = h->d_params;
   const float* dwk = base + h->spec.off[3 * layer];
   const float* pwk = base + h->spec.off[3 * layer + 1];
   const float* b = base + h->spec.off[3 * layer + 2];
   dim3 grid((Wo + 31) / 32, (Ho + 3) / 4, n), block(128);
   sep_layer_kernel<CIN, STRIDE, RAW, TIn><<<grid, block, 0, h->stream>>>(in, out, dwk, pwk, b, lut, pre_scale, pre_shift,
-                                                                        n, H, W, Ho, Wo, pad_t, pad_l);
+                                                                        n, H, W, Ho, Wo, pad_t, pad_l, in_mpad, out_mpad);
   LAUNCH_CHECK();
   return UBD_OK;
 }
@@ -281,7 +297,7 @@ static int run_stem(ubd_handle h, const void* d_img, int in_dtype, int preproc, 
   // the tensor-core layers read tf32: round (rna) where the map is produced instead of letting the
   // MMA truncate it
   rc = launch_sep<24, 2, false, float>(h, (const float*)act2, act3, 2, n, H2, W2, H4, W4, p2, p2, nullptr,
-                                       h->precision == UBD_TF32 ? -1.f : 0.f, 0.f);
+                                       h->precision == UBD_TF32 ? -1.f : 0.f, 0.f, 0, UBD_MAP_PAD);
   return rc;
 }
 
@@ -289,9 +305,9 @@ static int launch_dil_fp32(ubd_handle h, const float4* in, float4* out, const fl
                            const float4* gate, int n, int hh, int ww, int d, int mode) {
   dim3 grid((ww + DIL_TW - 1) / DIL_TW, (hh + DIL_TH - 1) / DIL_TH, n), block(128);
   const size_t smem = 9 * 24 * 24 * 4;
-  if (mode == 0) dilconv_fp32_kernel<true, true, false><<<grid, block, smem, h->stream>>>(in, out, w, b, nullptr, n, hh, ww, d);
-  else if (mode == 1) dilconv_fp32_kernel<false, false, true><<<grid, block, smem, h->stream>>>(in, out, w, nullptr, gate, n, hh, ww, d);
-  else dilconv_fp32_kernel<false, false, false><<<grid, block, smem, h->stream>>>(in, out, w, nullptr, nullptr, n, hh, ww, d);
+  if (mode == 0) dilconv_fp32_kernel<true, true, false><<<grid, block, smem, h->stream>>>(in, out, w, b, nullptr, n, hh, ww, d, UBD_MAP_PAD);
+  else if (mode == 1) dilconv_fp32_kernel<false, false, true><<<grid, block, smem, h->stream>>>(in, out, w, nullptr, gate, n, hh, ww, d, UBD_MAP_PAD);
+  else dilconv_fp32_kernel<false, false, false><<<grid, block, smem, h->stream>>>(in, out, w, nullptr, nullptr, n, hh, ww, d, UBD_MAP_PAD);
   LAUNCH_CHECK();
   return UBD_OK;
 }
@@ -300,31 +316,48 @@ static int launch_head(ubd_handle h, const float4* in, float* logits, uint8_t* m
   const float* hk = h->d_params + h->spec.off[21];
   const float* hb = h->d_params + h->spec.off[22];
   dim3 grid((unsigned)(((size_t)hh * ww + 127) / 128), n), block(128);
-  head_threshold_kernel<<<grid, block, 0, h->stream>>>(in, logits, mask, hk, hb, h->spec.n_out, thr, n, hh, ww);
+  head_threshold_kernel<<<grid, block, 0, h->stream>>>(in, logits, mask, hk, hb, h->spec.n_out, thr, n, hh, ww, UBD_MAP_PAD);
   LAUNCH_CHECK();
   return UBD_OK;
 }
 
 static int pick_chunk(ubd_handle h, int n, int H, int W) {
   if (h->opt_chunk > 0) return std::min(n, h->opt_chunk);
-  // Images per sweep through the layer stack.  Two opposing needs: enough work items per launch to
-  // fill 148 SMs evenly, and the two ping-pong quarter-resolution maps (2 * 96 B per map pixel per
-  // image) small enough to stay resident in the 126 MB L2 between layers.
+  // Images per sweep through the layer stack.  Measured on B200 (1024x1024 inputs, tf32): 2 -> 4.56 ms,
+  // 4 -> 2.33, 8 -> 2.00, 16 -> 1.82 ms for the six dilated layers of a 64-image batch: the per-launch
+  // fixed cost and the tail of the static item schedule outweigh L2 residency of the ping-pong maps,
+  // so take 16 images (more for small maps), bounded by ~1.6 GB of half-resolution stem scratch.
   const double per_img = (double)(H / 4) * (W / 4) * 2.0 * 96.0;
   int c = (int)(100e6 / per_img);
-  return std::max(1, std::min(n, std::min(c, 16)));
+  return std::max(1, std::min(n, std::max(c, 16)));
+}
+
+// The two ping-pong quarter-resolution maps.  Their zero x-padding is the convolution's zero padding,
+// so the buffers are cleared whenever they are (re)allocated or the map shape changes; kernels only
+// ever write the interior.
+static int ensure_maps(ubd_handle h, int n, int mh, int mw) {
+  const size_t bytes = act_elems(n, mh, mw, UBD_MAP_PAD) * sizeof(float4);
+  const bool grow = bytes > h->mapA.cap || bytes > h->mapB.cap;
+  ENSURE(h->mapA, bytes);
+  ENSURE(h->mapB, bytes);
+  if (grow || h->map_h != mh || h->map_w != mw || h->map_n < n) {
+    UBD_CUDA(cudaMemsetAsync(h->mapA.p, 0, h->mapA.cap, h->stream));
+    UBD_CUDA(cudaMemsetAsync(h->mapB.p, 0, h->mapB.cap, h->stream));
+    h->map_h = mh; h->map_w = mw; h->map_n = n;
+  }
+  return UBD_OK;
 }
 
 // d_img: device images.  d_logits (nullable) / d_mask (nullable): device outputs for the whole batch.
 static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
                           float* d_logits, uint8_t* d_mask, float thr) {
+  HostTimer ht_fwd(h, 0);
   const int h4 = H / 4, w4 = W / 4;
   const int chunk = pick_chunk(h, n, H, W);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
   ENSURE(h->act1, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
   ENSURE(h->act2, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
-  ENSURE(h->mapA, (size_t)chunk * UBD_NG * q_px * sizeof(float4));
-  ENSURE(h->mapB, (size_t)chunk * UBD_NG * q_px * sizeof(float4));
+  { int rc_ = ensure_maps(h, chunk, h4, w4); if (rc_) return rc_; }
   const size_t img_stride = (size_t)H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int cn = std::min(chunk, n - c0);
@@ -363,6 +396,7 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
   const int max_comps = h->opt_max_comps;
   const int max_pts = h->opt_max_points > 0 ? h->opt_max_points : (int)std::min<size_t>((size_t)n * npx / 2 + 1024, (size_t)1 << 26);
   ENSURE(h->parent, (size_t)n * pstride * sizeof(int));
+  ENSURE(h->outer, (size_t)n * pstride);
   ENSURE(h->labels, (size_t)n * npx * sizeof(int));
   ENSURE(h->slot_of, (size_t)n * npx * sizeof(int));
   ENSURE(h->comps, (size_t)n * max_comps * sizeof(CompRec));
@@ -382,13 +416,17 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
 
   dim3 tgrid((mw + 31) / 32, (mh + 7) / 8, n), tblock(256);
   dim3 lgrid((unsigned)((npx + 1 + 255) / 256), n);
+  HostTimer* ht_enq = new HostTimer(h, 1);
   ProfScope* ps_ccl = new ProfScope(h, &h->prof_ccl);
   UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
   ccl_init_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
   ccl_merge1_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, labels, mh, mw, pstride); LAUNCH_CHECK();
+  uint8_t* outer = (uint8_t*)h->outer.p;
+  ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+  dim3 bgrid((unsigned)((2 * (mh + mw) + 255) / 256), n);
+  ccl_mark_outer_kernel<<<bgrid, 256, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+  ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, outer, labels, mh, mw, pstride); LAUNCH_CHECK();
   ccl_slots_kernel<<<n, 1024, 0, h->stream>>>(labels, slot_of, comps, cls_sums, n_cls, d_ncomps, mh, mw, max_comps); LAUNCH_CHECK();
   dim3 sgrid((mw + 1 + 31) / 32, (mh + 1 + 7) / 8, n);
   ccl_stats_kernel<<<sgrid, tblock, 0, h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls, mh, mw, max_comps); LAUNCH_CHECK();
@@ -398,6 +436,8 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
   ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)h->hull_pts.p,
                                                      d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();
   delete ps_ccl;
+  delete ht_enq;
+  HostTimer* ht_s1 = new HostTimer(h, 2);
 
   // header: kept counts per image + totals (one small D2H), then the records and hull points
   std::vector<int> header(n + sizeof(CclTotals) / sizeof(int));
@@ -405,6 +445,7 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
   if (labels_out_host)
     UBD_CUDA(cudaMemcpyAsync(labels_out_host, labels, (size_t)n * npx * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
+  delete ht_s1;
   CclTotals tot;
   memcpy(&tot, header.data() + n, sizeof(tot));
   if (tot.max_ncomp > max_comps)
@@ -416,28 +457,41 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
     UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_pts) + " hull candidate points exceed max_points " + std::to_string(max_pts));
   for (int i = 0; i < n; ++i) n_comps_per_image[i] = header[i];
   if (tot.total_kept == 0) return UBD_OK;
+  HostTimer* ht_s2 = new HostTimer(h, 3);
   std::vector<OutRec> recs(tot.total_kept);
   std::vector<HullPt> pts(tot.total_pts);
   UBD_CUDA(cudaMemcpyAsync(recs.data(), h->out_recs.p, recs.size() * sizeof(OutRec), cudaMemcpyDeviceToHost, h->stream));
   if (!pts.empty())
     UBD_CUDA(cudaMemcpyAsync(pts.data(), h->hull_pts.p, pts.size() * sizeof(HullPt), cudaMemcpyDeviceToHost, h->stream));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
-  // group the hull candidates by component (counting sort), then boxes on the host
-  std::vector<int> start(tot.total_kept + 1, 0);
-  for (const HullPt& p : pts) start[p.comp + 1]++;
-  for (int i = 0; i < tot.total_kept; ++i) start[i + 1] += start[i];
-  std::vector<int32_t> xy(2 * pts.size());
-  std::vector<int> fill(start.begin(), start.end() - 1);
+  delete ht_s2;
+  HostTimer ht_host(h, 4);
+  // Reduce the hull candidates to the leftmost / rightmost one per (component, row) -- only those can
+  // be hull vertices -- then the min-area box of each component on the host.
+  std::vector<int> row0(tot.total_kept + 1, 0);
+  for (int i = 0; i < tot.total_kept; ++i) row0[i + 1] = row0[i] + (recs[i].ymax - recs[i].ymin + 1);
+  std::vector<int> ext(2 * (size_t)row0[tot.total_kept]);
+  for (size_t k = 0; k < ext.size(); k += 2) { ext[k] = 0x7fffffff; ext[k + 1] = -1; }
   for (const HullPt& p : pts) {
-    const int k = fill[p.comp]++;
-    xy[2 * k] = p.xy & 0xffff; xy[2 * k + 1] = p.xy >> 16;
+    const int x = p.xy & 0xffff, y = p.xy >> 16;
+    int* e = &ext[2 * (size_t)(row0[p.comp] + y - recs[p.comp].ymin)];
+    if (x < e[0]) e[0] = x;
+    if (x > e[1]) e[1] = x;
   }
+  std::vector<int32_t> xy;
   for (int i = 0; i < tot.total_kept; ++i) {
     const OutRec& r = recs[i];
     ubd_component& c = comps_out[i];
     c.image = r.image; c.label = r.label; c.xmin = r.xmin; c.ymin = r.ymin; c.xmax = r.xmax; c.ymax = r.ymax;
     c.n_pixels = r.n_pixels; c.n_filled = r.n_filled; c.area_x2 = r.area_x2; c.class_id = r.class_id;
-    ubd_min_area_box(xy.data() + 2 * start[i], start[i + 1] - start[i], c.box);
+    xy.clear();
+    for (int y = r.ymin; y <= r.ymax; ++y) {
+      const int* e = &ext[2 * (size_t)(row0[i] + y - r.ymin)];
+      if (e[1] < 0) continue;
+      xy.push_back(e[0]); xy.push_back(y);
+      if (e[1] != e[0]) { xy.push_back(e[1]); xy.push_back(y); }
+    }
+    ubd_min_area_box(xy.data(), (int)(xy.size() / 2), c.box);
   }
   return UBD_OK;
 }
@@ -554,7 +608,7 @@ __global__ void nhwc_to_planar_kernel(const float* __restrict__ src, float4* __r
   const size_t img = i / npx, p = i % npx;
   for (int g = 0; g < UBD_NG; ++g) {
     const float* s = src + i * UBD_NF + 4 * g;
-    dst[(img * UBD_NG + g) * npx + p] = make_float4(s[0], s[1], s[2], s[3]);
+    dst[act_index((int)img, g, (int)(p / ww), (int)(p % ww), hh, ww, UBD_MAP_PAD)] = make_float4(s[0], s[1], s[2], s[3]);
   }
 }
 __global__ void planar_to_nhwc_kernel(const float4* __restrict__ src, float* __restrict__ dst, int n, int hh, int ww) {
@@ -563,7 +617,7 @@ __global__ void planar_to_nhwc_kernel(const float4* __restrict__ src, float* __r
   if (i >= (size_t)n * npx) return;
   const size_t img = i / npx, p = i % npx;
   for (int g = 0; g < UBD_NG; ++g) {
-    const float4 v = src[(img * UBD_NG + g) * npx + p];
+    const float4 v = src[act_index((int)img, g, (int)(p / ww), (int)(p % ww), hh, ww, UBD_MAP_PAD)];
     float* d = dst + i * UBD_NF + 4 * g;
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
@@ -578,8 +632,7 @@ extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float
   UBD_CUDA(cudaSetDevice(h->device));
   const size_t elems = (size_t)n * mh * mw * UBD_NF;
   ENSURE(h->t_scratch, elems * sizeof(float));
-  ENSURE(h->mapA, elems * sizeof(float));
-  ENSURE(h->mapB, elems * sizeof(float));
+  { int rc_ = ensure_maps(h, n, mh, mw); if (rc_) return rc_; }
   UBD_CUDA(cudaMemcpyAsync(h->t_scratch.p, in_nhwc, elems * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   const unsigned blocks = (unsigned)(((size_t)n * mh * mw + 255) / 256);
   nhwc_to_planar_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->t_scratch.p, (float4*)h->mapA.p, n, mh, mw); LAUNCH_CHECK();
@@ -599,6 +652,15 @@ extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float
   UBD_CUDA(cudaMemcpyAsync(out_nhwc, h->t_scratch.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
   return precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
+}
+
+extern "C" int ubd_debug_read_trace(ubd_handle h, long long* out, int n_values) {
+  if (!h || !out || !h->tc_trace.p) return UBD_ERR_ARG;
+  UBD_CUDA(cudaSetDevice(h->device));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  UBD_CUDA(cudaMemcpy(out, h->tc_trace.p, std::min<size_t>((size_t)n_values * 8, 3 * 1024 * 4 * 8), cudaMemcpyDeviceToHost));
+  UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap));
+  return UBD_OK;
 }
 
 #include "ubd_train_api.inc"

@@ -1,8 +1,8 @@
 // GPU connected components with cv2.findContours(RETR_EXTERNAL) semantics (utils.py:51-60,
 // segmap_manager.py:54-69; exact statement in SURVEY.md 8a/P2 and oracle/postproc.py::ccl_spec):
-//   1. union-find over all pixels: foreground 8-connected, background 4-connected, border
-//      background joined to a virtual outside node V = h*w;
-//   2. "filled" = foreground or background not in V's set (holes); union 8-adjacent filled pixels;
+//   1. union-find over all pixels: foreground 8-connected, background 4-connected; the background
+//      sets that own a border pixel are flagged "outer" (connected to the outside of the image);
+//   2. "filled" = foreground or background whose set is not outer (holes); union 8-adjacent filled;
 //   3. label = root = smallest raster index of the filled component (first pixel in raster order);
 //   4. per-component reductions: bbox, foreground / filled pixel counts, 2x2 bit-quad counts
 //      (2*contourArea = 2*#Q4 + #Q3), class-probability sums over the filled pixels.
@@ -56,7 +56,6 @@ ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int 
     const int start = below ? 32 - __clz(below) : 0;         // first lane of my run
     par[(size_t)y * w + x] = y * w + (x - (int)lane + start);
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) par[h * w] = h * w;   // outside node
 }
 
 // Phase 1: foreground 8-connectivity, background 4-connectivity (+ border background ~ outside).
@@ -84,37 +83,54 @@ ccl_merge1_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, in
   } else {
     if (hasN && m[p - w] == 0) uf_union(par, p, p - w);
     if (hasW && (x & 31) == 0 && m[p - 1] == 0) uf_union(par, p, p - 1);
-    if (!hasW || !hasN || !hasE || y == h - 1) uf_union(par, p, h * w);
   }
 }
 
-// Full path compression: parent[p] = root(p) (also for the outside node).
+// Full path compression: parent[p] = root(p); clears the outer flags for the next kernel.
 __global__ void __launch_bounds__(256)
-ccl_flatten_kernel(int* __restrict__ parent, int h, int w, size_t pstride) {
+ccl_flatten_kernel(int* __restrict__ parent, uint8_t* __restrict__ outer, int h, int w, size_t pstride) {
   const int n = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > h * w) return;
+  if (i >= h * w) return;
   int* par = parent + (size_t)n * pstride;
   par[i] = uf_find(par, i);
+  outer[(size_t)n * pstride + i] = 0;
 }
 
-// Phase 2: 8-connectivity over filled pixels.  Requires flattened parents from phase 1 (then a
-// non-root's parent never changes again and background p is outer iff parent[p] == parent[V]).
+// outer[root] = 1 for every background set that owns a pixel on the image border (those are
+// 4-connected to the outside); plain stores of the same value, no atomics.  Needs flattened parents.
+__global__ void __launch_bounds__(256)
+ccl_mark_outer_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ parent,
+                      uint8_t* __restrict__ outer, int h, int w, size_t pstride) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // index along the border: 2w + 2h
+  int y, x;
+  if (i < w) { y = 0; x = i; }
+  else if (i < 2 * w) { y = h - 1; x = i - w; }
+  else if (i < 2 * w + h) { y = i - 2 * w; x = 0; }
+  else if (i < 2 * w + 2 * h) { y = i - 2 * w - h; x = w - 1; }
+  else return;
+  const int p = y * w + x;
+  if (mask[(size_t)n * h * w + p] == 0) outer[(size_t)n * pstride + parent[(size_t)n * pstride + p]] = 1;
+}
+
+// Phase 2: 8-connectivity over filled pixels.  Requires flattened parents from phase 1: then a
+// non-root's parent never changes again, and a hole root is only ever re-parented inside its own
+// filled set, so "background q is outer" == outer[parent[q]] at any time during this kernel.
 // Pairs of two foreground pixels are already connected by phase 1 and are skipped.
 __global__ void __launch_bounds__(256)
-ccl_merge2_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+ccl_merge2_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, const uint8_t* __restrict__ outer,
+                  int h, int w, size_t pstride) {
   const int n = blockIdx.z;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const uint8_t* m = mask + (size_t)n * h * w;
   int* par = parent + (size_t)n * pstride;
-  const int rootV = *((volatile int*)(par + h * w));
+  const uint8_t* out = outer + (size_t)n * pstride;
   const int p = y * w + x;
   const bool fg = m[p] != 0;
-  // a hole pixel's parent is either its (former) hole root or, if it is that root, something in
-  // its filled set; neither can equal rootV.
-  auto filled = [&](int q) -> bool { return m[q] != 0 || *((volatile int*)(par + q)) != rootV; };
+  auto filled = [&](int q) -> bool { return m[q] != 0 || out[*((volatile int*)(par + q))] == 0; };
   if (!fg && !filled(p)) return;
   const bool hasW = x > 0, hasN = y > 0, hasE = x < w - 1;
   auto link = [&](int q) { if (!(fg && m[q] != 0)) uf_union(par, p, q); };
@@ -127,18 +143,17 @@ ccl_merge2_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, in
   }
 }
 
-// labels[p] = filled ? root : -1.
+// labels[p] = filled ? root : -1.  An outer background pixel was never re-parented, so its parent is
+// still its phase-1 root and carries the outer flag; everything else is a filled pixel.
 __global__ void __launch_bounds__(256)
-ccl_label_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int* __restrict__ labels,
-                 int h, int w, size_t pstride) {
+ccl_label_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, const uint8_t* __restrict__ outer,
+                 int* __restrict__ labels, int h, int w, size_t pstride) {
   const int n = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   int* par = parent + (size_t)n * pstride;
-  const int rootV = uf_find(par, h * w);
-  const int r = uf_find(par, i);
-  const bool filled = mask[(size_t)n * h * w + i] != 0 || r != rootV;
-  labels[(size_t)n * h * w + i] = filled ? r : -1;
+  const bool filled = mask[(size_t)n * h * w + i] != 0 || outer[(size_t)n * pstride + par[i]] == 0;
+  labels[(size_t)n * h * w + i] = filled ? uf_find(par, i) : -1;
 }
 
 // One CTA per image: rank the roots in raster order -> slot_of[root], n_comps[n]; initialise records.
@@ -357,8 +372,10 @@ ccl_compact_kernel(const CompRec* __restrict__ comps, const unsigned long long* 
   }
 }
 
-// Run end points of kept components: every convex-hull vertex of a component is the first or last
-// pixel of one of its row runs, so these are all cv2.minAreaRect needs (utils.py:56).
+// Hull candidates of kept components.  A convex-hull vertex of a component uniquely maximises u.q
+// over its pixels for some direction u, so its neighbour in the x-direction of u and its neighbour
+// in the y-direction of u are both outside the component: only such corner pixels are emitted
+// (a superset of the hull vertices, all that cv2.minAreaRect needs, utils.py:56).
 struct HullPt { int comp; int xy; };     // comp = index into the compacted output; xy = (y << 16) | x
 __global__ void __launch_bounds__(256)
 ccl_points_kernel(const int* __restrict__ labels, const int* __restrict__ slot_of,
@@ -372,9 +389,11 @@ ccl_points_kernel(const int* __restrict__ labels, const int* __restrict__ slot_o
     const int* lab = labels + (size_t)n * h * w;
     const int l = lab[y * w + x];
     if (l >= 0) {
-      const bool left_end = x == 0 || lab[y * w + x - 1] != l;
-      const bool right_end = x == w - 1 || lab[y * w + x + 1] != l;
-      if (left_end || right_end) {
+      const bool wo = x == 0 || lab[y * w + x - 1] != l;
+      const bool eo = x == w - 1 || lab[y * w + x + 1] != l;
+      const bool no = y == 0 || lab[(y - 1) * w + x] != l;
+      const bool so = y == h - 1 || lab[(y + 1) * w + x] != l;
+      if ((wo || eo) && (no || so)) {
         const int slot = slot_of[(size_t)n * h * w + l];
         if (slot < max_comps) comp = out_index_of_slot[(size_t)n * max_comps + slot];
       }

@@ -11,11 +11,20 @@
 #define UBD_NG 6           // 24 channels = 6 planes of 4 fp32 (one 16-byte unit per pixel and plane)
 #define UBD_NLAYERS_DIL 6  // net.py:298-304
 
-// Feature maps live in HBM as "planar-by-4": act[n][g][y][x] of float4 (channels 4g..4g+3).
-// One pixel of one plane is 16 bytes = one shared-memory core-matrix row of the tcgen05 K-major
-// no-swizzle layout, so a (dy,dx) tap shift is a pure address offset for every kernel.
-__host__ __device__ __forceinline__ size_t act_index(int n, int g, int y, int x, int H, int W) {
-  return ((size_t)(n * UBD_NG + g) * H + y) * W + x;
+// Feature maps live in HBM as row-interleaved planes of float4 with x padding:
+//   act[n][y][g][xp], g = 0..5 (channels 4g..4g+3), xp = x + pad, row pitch Wp = W + 2*pad.
+// One pixel of one plane is 16 bytes = one row of a UMMA core matrix of the K-major no-swizzle
+// layout, so a (dy,dx) tap is a pure address offset.  The pad columns are zero (buffers are zeroed
+// when (re)shaped and every kernel writes the interior only): they are the conv zero padding in x,
+// and they make the six planes of one image row ONE contiguous block that the TMA unit stages with a
+// single cp.async.bulk.  Quarter-resolution maps use pad = UBD_MAP_PAD (largest dilation);
+// the stem's half-resolution maps use pad = 0.
+#define UBD_MAP_PAD 16
+__host__ __device__ __forceinline__ size_t act_index(int n, int g, int y, int x, int H, int W, int pad) {
+  return (((size_t)n * H + y) * UBD_NG + g) * (size_t)(W + 2 * pad) + pad + x;
+}
+__host__ __device__ __forceinline__ size_t act_elems(int n, int H, int W, int pad) {
+  return (size_t)n * H * UBD_NG * (size_t)(W + 2 * pad);
 }
 
 struct WeightSpec {

@@ -25,7 +25,7 @@ sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
                  const float* __restrict__ bias,  // [24]
                  const float* __restrict__ lut,   // RAW u8: 256-entry preprocessing table (or null)
                  float pre_scale, float pre_shift,
-                 int N, int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
+                 int N, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int in_mpad, int out_mpad) {
   __shared__ float s_dw[9 * CIN];
   __shared__ __align__(16) float s_pw[CIN * UBD_NF];
   __shared__ float s_b[UBD_NF];
@@ -72,7 +72,7 @@ sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
         const float4* p = reinterpret_cast<const float4*>(in);
 #pragma unroll
         for (int g = 0; g < CIN / 4; ++g) {
-          const float4 v = ldg4(&p[act_index(n, g, iy, ix, H, W)]);
+          const float4 v = ldg4(&p[act_index(n, g, iy, ix, H, W, in_mpad)]);
           d[4 * g + 0] = fmaf(v.x, wk[4 * g + 0], d[4 * g + 0]);
           d[4 * g + 1] = fmaf(v.y, wk[4 * g + 1], d[4 * g + 1]);
           d[4 * g + 2] = fmaf(v.z, wk[4 * g + 2], d[4 * g + 2]);
@@ -96,7 +96,7 @@ sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
     if (!RAW && pre_scale < 0.f) {     // producer-side rounding to the tf32 grid for the tensor-core layers
       a.x = rna_tf32(a.x); a.y = rna_tf32(a.y); a.z = rna_tf32(a.z); a.w = rna_tf32(a.w);
     }
-    out[act_index(n, og, y, x, Ho, Wo)] = a;
+    out[act_index(n, og, y, x, Ho, Wo, out_mpad)] = a;
   }
 }
 
@@ -115,7 +115,7 @@ dilconv_fp32_kernel(const float4* __restrict__ in, float4* __restrict__ out,
                     const float* __restrict__ wts,    // [9][24][24]
                     const float* __restrict__ bias,   // [24]
                     const float4* __restrict__ gate,  // same layout as out (GATE): out *= (gate > 0)
-                    int N, int H, int W, int d) {
+                    int N, int H, int W, int d, int mpad) {
   extern __shared__ __align__(16) float s_w[];        // 9*24*24 floats
   for (int i = threadIdx.x; i < 9 * UBD_NF * UBD_NF / 4; i += blockDim.x)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wts) + i);
@@ -143,7 +143,7 @@ dilconv_fp32_kernel(const float4* __restrict__ in, float4* __restrict__ out,
 #pragma unroll
       for (int p = 0; p < DIL_P; ++p) {
         const int yy = y0 + 4 * p + dy;
-        v[p] = (xok && yy >= 0 && yy < H) ? ldg4(&in[act_index(n, g, yy, xx, H, W)])
+        v[p] = (xok && yy >= 0 && yy < H) ? ldg4(&in[act_index(n, g, yy, xx, H, W, mpad)])
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -173,7 +173,7 @@ dilconv_fp32_kernel(const float4* __restrict__ in, float4* __restrict__ out,
     for (int og = 0; og < UBD_NG; ++og) {
       float4 a = make_float4(acc[p][4 * og], acc[p][4 * og + 1], acc[p][4 * og + 2], acc[p][4 * og + 3]);
       if (RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-      const size_t idx = act_index(n, og, y, x, H, W);
+      const size_t idx = act_index(n, og, y, x, H, W, mpad);
       if (GATE) {
         const float4 gt = ldg4(&gate[idx]);
         a.x = gt.x > 0.f ? a.x : 0.f; a.y = gt.y > 0.f ? a.y : 0.f;
@@ -191,7 +191,7 @@ dilconv_fp32_kernel(const float4* __restrict__ in, float4* __restrict__ out,
 __global__ void __launch_bounds__(128)
 head_threshold_kernel(const float4* __restrict__ in, float* __restrict__ logits,
                       uint8_t* __restrict__ mask, const float* __restrict__ hk,   // [24][n_out]
-                      const float* __restrict__ hb, int n_out, float thr, int N, int H, int W) {
+                      const float* __restrict__ hb, int n_out, float thr, int N, int H, int W, int mpad) {
   __shared__ float s_k[UBD_NF * (1 + UBD_MAX_CLASSES)];
   __shared__ float s_b[1 + UBD_MAX_CLASSES];
   for (int i = threadIdx.x; i < UBD_NF * n_out; i += blockDim.x) s_k[i] = hk[i];
@@ -201,10 +201,11 @@ head_threshold_kernel(const float4* __restrict__ in, float* __restrict__ logits,
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (p >= npx) return;
+  const int y = (int)(p / W), x = (int)(p % W);
   float v[UBD_NF];
 #pragma unroll
   for (int g = 0; g < UBD_NG; ++g) {
-    const float4 a = ldg4(&in[((size_t)(n * UBD_NG + g)) * npx + p]);
+    const float4 a = ldg4(&in[act_index(n, g, y, x, H, W, mpad)]);
     v[4 * g] = a.x; v[4 * g + 1] = a.y; v[4 * g + 2] = a.z; v[4 * g + 3] = a.w;
   }
   float* lo = logits ? logits + ((size_t)n * npx + p) * n_out : nullptr;

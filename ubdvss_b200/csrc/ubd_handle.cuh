@@ -18,6 +18,7 @@ struct ubd_handle_s {
   bool profile = false;
   struct Prof { double ms = 0; int64_t launches = 0; };
   Prof prof_dil, prof_stem, prof_ccl, prof_head;
+  double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wall-clock of host phases (option "profile")
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<std::pair<Prof*, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
   std::string err;
@@ -35,7 +36,10 @@ struct ubd_handle_s {
   // inference workspaces
   DevBuf d_images, d_logits, d_mask;
   DevBuf act1, act2, mapA, mapB;
+  int map_h = 0, map_w = 0, map_n = 0;     // shape the padded maps were last zeroed for
+  DevBuf outer;
   DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
+  DevBuf tc_trace;                // optional event trace of CTA 0 (option "tc_trace")
   DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
   // training workspaces
   DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss;
@@ -44,8 +48,8 @@ struct ubd_handle_s {
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 
   std::vector<DevBuf*> all_bufs() {
-    return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &t_acts, &t_grads_act,
+    return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &outer, &parent, &labels, &slot_of, &comps,
+            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc_trace, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
   }
 };

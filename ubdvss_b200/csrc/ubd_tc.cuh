@@ -3,24 +3,27 @@
 // GEMM view of one output row segment:  D[128 px, 32 oc] += A[128 px, K] * B[K, 32 oc],
 //   K = 9 taps x 24 channels; kind::tf32 consumes K = 8 per instruction -> 27 MMAs per segment.
 //
-// Operand A is the input feature map itself.  Maps are "planar-by-4" in HBM (act[n][g][y][x] float4),
-// so one pixel of one plane is 16 bytes = one row of a UMMA core matrix (8 rows x 16 B) of the
-// K-major SWIZZLE_NONE canonical layout ((8,m),2):((16 B, SBO),LBO).  A row slot in shared memory
-// is [6 planes][160 px][16 B]; 8 consecutive pixels form a core matrix (SBO = 128 B), the two K
-// cores of one MMA are two adjacent channel planes (LBO = plane stride).  A (dy,dx) tap is then
-// nothing but a different descriptor start address: slot(row + dy) + (16 + dx*d) * 16 B.
-// No im2col copy exists anywhere.
+// Operand A is the input feature map itself.  Maps are row-interleaved planes of float4 with zero x
+// padding (ubd_common.cuh), so one pixel of one plane is 16 bytes = one row of a UMMA core matrix
+// (8 rows x 16 B) of the K-major SWIZZLE_NONE canonical layout ((8,m),2):((16 B, SBO),LBO).  A row
+// slot in shared memory is an image of one map row: [6 planes][SW + 32 px][16 B]; 8 consecutive
+// pixels form a core matrix (SBO = 128 B), the two K cores of one MMA are two adjacent channel
+// planes (LBO = plane stride).  A (dy,dx) tap is then nothing but a different descriptor start
+// address: slot(row + dy) + (16 + dx*d) * 16 B.  No im2col copy exists anywhere.
 //
 // Dilation is handled by phase decomposition in y: the rows r, r+d, r+2d, ... of an image form an
 // independent 1-dilated problem, so a CTA walks a phase top to bottom with a ring of row slots:
-// each input row is fetched once (+2 halo rows per item) and used by three output rows.  Rows are
-// staged by the TMA unit with cp.async.bulk (one contiguous 16*(128+2d)-byte run per plane, image
-// borders filled from a zero page), completion on mbarriers.
+// each input row is fetched once (+2 halo rows per item) and used by three output rows.  A row is
+// staged by the TMA unit with cp.async.bulk: ONE copy when the strip spans the padded row (maps up
+// to 256 px wide), else one per plane; rows above / below the image come from a zero page;
+// completion is signalled on mbarriers.
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over a static item list):
+// Warp roles (192 threads, 1 CTA/SM, persistent over a static item list).  Role code is
+// warp-uniform; only the asynchronous instruction itself sits under elect.sync, so descriptors live
+// in uniform registers and an MMA costs a handful of issue slots:
 //   warp 0   : producer  - bulk copies into the slot ring      (empty[] -> full[])
-//   warp 1   : MMA issue - one elected lane, 27 tcgen05.mma per segment into a TMEM accumulator,
-//              tcgen05.commit to tmem_full[] and to the empty[] of the row that is no longer needed
+//   warp 1   : MMA issue - 27 tcgen05.mma per segment into a TMEM accumulator, tcgen05.commit to
+//              tmem_full[] and to the empty[] of the row that is no longer needed
 //   warps 2-5: epilogue  - tcgen05.ld (lane = pixel, 24 columns = channels), bias + ReLU,
 //              six coalesced float4 stores (one per plane)
 #pragma once
@@ -28,12 +31,12 @@
 
 namespace tc {
 
-constexpr int TW = 128;                       // pixels per segment = UMMA M
-constexpr int HALO = 16;                      // largest dilation
-constexpr int BW = TW + 2 * HALO;             // pixels per plane in a slot
-constexpr int PLANE_BYTES = BW * 16;          // 2560
-constexpr int SLOT_BYTES = UBD_NG * PLANE_BYTES;   // 15360
-constexpr int NS = 8;                         // row slots in the ring
+constexpr int SEG = 128;                      // pixels per MMA segment = UMMA M
+constexpr int MAX_SW = 256;                   // widest strip: two segments per staged row
+constexpr int PAD = UBD_MAP_PAD;              // 16 = largest dilation
+constexpr int MAX_PLANE_BYTES = (MAX_SW + 2 * PAD) * 16;        // 4608
+constexpr int MAX_SLOT_BYTES = UBD_NG * MAX_PLANE_BYTES;         // 27648
+constexpr int NS = 6;                         // row slots in the ring
 constexpr int NACC = 4;                       // TMEM accumulator stages
 constexpr int UMMA_N = 32;                    // 24 output channels padded to a legal N for M=128
 constexpr int TMEM_COLS = NACC * UMMA_N;      // 128
@@ -43,10 +46,10 @@ constexpr int W_BYTES = N_MMA * B_TILE_BYTES; // 27648
 constexpr int WB_BYTES = W_BYTES + 128;       // + bias[24] padded to 32 floats
 constexpr int RQ = 8;                         // output rows per work item
 constexpr int THREADS = 192;
-constexpr int ZERO_BYTES = PLANE_BYTES;
+constexpr int ZERO_BYTES = MAX_SLOT_BYTES;
 
 struct Smem {
-  uint8_t slots[NS * SLOT_BYTES];
+  uint8_t slots[NS * MAX_SLOT_BYTES];
   uint8_t wimg[W_BYTES];
   float bias[32];
   uint64_t full[NS], empty[NS], tfull[NACC], tempty[NACC], wbar;
@@ -57,6 +60,15 @@ constexpr size_t SMEM_BYTES = sizeof(Smem) + 128;    // + manual 128 B alignment
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -66,9 +78,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a wrong descriptor / byte count must end in an error code, never in a hung GPU.
+// Bounded wait, executed by every lane of the role's warp; the result is made warp-uniform with a
+// vote so that everything downstream stays in the uniform datapath.  A wrong descriptor / byte count
+// ends in an error code (host: tc_check_error), never in a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code) {
   const long long t0 = clock64();
+  bool ok = true;
   while (true) {
     uint32_t done;
     asm volatile(
@@ -76,10 +91,11 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return true;
-    if (*abort_flag) return false;
-    if (clock64() - t0 > 1500000000LL) { atomicCAS(gerr, 0, code); *abort_flag = 1; return false; }
+    if (done) break;
+    if (*abort_flag) { ok = false; break; }
+    if (clock64() - t0 > 1500000000LL) { atomicCAS(gerr, 0, code); *abort_flag = 1; ok = false; break; }
   }
+  return __all_sync(0xffffffffu, ok);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -91,13 +107,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// lo word = start address >> 4 | (LBO >> 4) << 16, hi word = SBO >> 4 | version bit 14.
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 32 (cute::UMMA::InstrDescriptor).
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((UMMA_N >> 3) << 17) | ((TW >> 4) << 24);
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((UMMA_N >> 3) << 17) | ((SEG >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -107,23 +122,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_TF32), "r"(accumulate), "r"(0u) : "memory");
 }
 
-struct Item { int n, x0, r, q0, rows, nq; };
+struct Item { int n, x0, r, q0, rows, nq, nseg, copy_px; };
 
 struct Sched {
-  int n_imgs, h, w, d, n_strips, n_chunks, total;
-  __device__ Sched(int n_imgs_, int h_, int w_, int d_) : n_imgs(n_imgs_), h(h_), w(w_), d(d_) {
-    n_strips = (w + TW - 1) / TW;
+  int n_imgs, h, w, d, sw, n_strips, n_chunks, total;
+  __device__ Sched(int n_imgs_, int h_, int w_, int d_, int sw_) : n_imgs(n_imgs_), h(h_), w(w_), d(d_), sw(sw_) {
+    n_strips = (w + sw - 1) / sw;
     n_chunks = ((h + d - 1) / d + RQ - 1) / RQ;
     total = n_imgs * n_strips * d * n_chunks;
   }
   __device__ bool get(int idx, Item& it) const {
     const int c = idx % n_chunks; int t = idx / n_chunks;
     it.r = t % d; t /= d;
-    it.x0 = (t % n_strips) * TW;
+    it.x0 = (t % n_strips) * sw;
     it.n = t / n_strips;
     it.nq = it.r < h ? (h - it.r + d - 1) / d : 0;
     it.q0 = c * RQ;
     it.rows = min(RQ, it.nq - it.q0);
+    const int valid = min(sw, w - it.x0);                 // output pixels of this strip
+    it.nseg = (valid + SEG - 1) / SEG;
+    it.copy_px = min(sw, w - it.x0) + 2 * PAD;            // padded pixels staged per plane
     return it.rows > 0;
   }
 };
@@ -134,14 +152,21 @@ __device__ __forceinline__ float round_tf32(float v) {
   return __uint_as_float(u);
 }
 
-// in/out: planar-by-4 maps of n_imgs images; wb: this layer's B image (W_BYTES) followed by bias[32].
+// in/out: padded row-interleaved maps (pad = PAD) of n_imgs images; wb: this layer's B image
+// (W_BYTES) followed by bias[32]; sw: strip width (128 or 256).
 __global__ void __launch_bounds__(THREADS, 1)
 dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, const uint8_t* __restrict__ wb,
-                    const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int round_out, int* gerr) {
+                    const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int round_out, int* gerr,
+                    long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   volatile int* abort_flag = &S.abort_flag;
+  // optional event trace of CTA 0 (bring-up / tuning): trace[role][event][4] cycle stamps
+  const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
+  int tr_n = 0;
+#define TC_TRACE(role, slot, val) do { if (tr && tr_n < 1024) trace[((role) * 1024 + tr_n) * 4 + (slot)] = (val); } while (0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 1); }
@@ -157,89 +182,111 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = S.tmem_base;
-  const Sched sched(n_imgs, h, w, d);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+  const Sched sched(n_imgs, h, w, d, sw);
   const uint32_t slots0 = smem_u32(S.slots);
+  const int wp = w + 2 * PAD;                              // global row pitch in pixels
+  const uint32_t plane_bytes = (uint32_t)(sw + 2 * PAD) * 16;   // slot plane stride = LBO
+  const uint32_t slot_bytes = UBD_NG * plane_bytes;
+  const bool one_copy = (w == sw);                         // slot is an exact image of the global row block
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer (one lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ producer
+    if (elect_one()) {
       mbar_expect_tx(smem_u32(&S.wbar), WB_BYTES);
       bulk_g2s(smem_u32(S.wimg), wb, WB_BYTES, smem_u32(&S.wbar));
-      const uint32_t row_px = TW + 2 * d;
-      const uint32_t row_bytes = UBD_NG * row_px * 16;
-      uint32_t lseq = 0;
-      bool ok = true;
-      for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
-        Item it;
-        if (!sched.get(idx, it)) continue;
-        const int xl = it.x0 - d, xr = it.x0 + TW + d;
-        const int cl = max(xl, 0), cr = min(xr, w);
-        const uint32_t nleft = cl - xl, ndata = cr - cl, nright = xr - cr;
-        for (int q = it.q0 - 1; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
-          const uint32_t slot = lseq % NS;
-          ok = mbar_wait(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 1);
-          if (!ok) break;
-          const uint32_t bar = smem_u32(&S.full[slot]);
+    }
+    uint32_t lseq = 0;
+    bool ok = true;
+    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+      Item it;
+      if (!sched.get(idx, it)) continue;
+      const uint32_t copy_bytes = (uint32_t)it.copy_px * 16;
+      const uint32_t row_bytes = one_copy ? slot_bytes : UBD_NG * copy_bytes;
+      for (int q = it.q0 - 1; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
+        const uint32_t slot = lseq % NS;
+        TC_TRACE(0, 0, clock64());
+        ok = mbar_wait(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 1);
+        if (!ok) break;
+        TC_TRACE(0, 1, clock64());
+        const uint32_t bar = smem_u32(&S.full[slot]);
+        const uint32_t dst = slots0 + slot * slot_bytes;
+        const bool valid = q >= 0 && q < it.nq;
+        // source of plane 0: padded pixel x0 of row y (the strip's left halo starts there)
+        const float4* src = valid ? in + (((size_t)it.n * h + (it.r + q * d)) * UBD_NG) * wp + it.x0
+                                  : reinterpret_cast<const float4*>(zeros);
+        if (elect_one()) {
           mbar_expect_tx(bar, row_bytes);
-          const uint32_t dst0 = slots0 + slot * SLOT_BYTES + (HALO - d) * 16;
-          if (q < 0 || q >= it.nq) {
-#pragma unroll
-            for (int g = 0; g < UBD_NG; ++g) bulk_g2s(dst0 + g * PLANE_BYTES, zeros, row_px * 16, bar);
+          if (one_copy) {
+            bulk_g2s(dst, src, slot_bytes, bar);
           } else {
-            const int y = it.r + q * d;
 #pragma unroll
-            for (int g = 0; g < UBD_NG; ++g) {
-              const uint32_t dst = dst0 + g * PLANE_BYTES;
-              if (nleft) bulk_g2s(dst, zeros, nleft * 16, bar);
-              bulk_g2s(dst + nleft * 16, in + act_index(it.n, g, y, cl, h, w), ndata * 16, bar);
-              if (nright) bulk_g2s(dst + (nleft + ndata) * 16, zeros, nright * 16, bar);
-            }
+            for (int g = 0; g < UBD_NG; ++g)
+              bulk_g2s(dst + g * plane_bytes, valid ? src + (size_t)g * wp : src, copy_bytes, bar);
           }
         }
+        __syncwarp();
+        TC_TRACE(0, 2, clock64());
+        ++tr_n;
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
-      bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 2);
-      const uint32_t wsm = smem_u32(S.wimg);
-      uint32_t lbase = 0, oseq = 0, waited = 0;      // waited = number of row loads known to have landed
-      for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
-        Item it;
-        if (!sched.get(idx, it)) continue;
-        for (int j = 0; j < it.rows && ok; ++j, ++oseq) {
-          while (waited < lbase + j + 3 && ok) {
-            ok = mbar_wait(smem_u32(&S.full[waited % NS]), (waited / NS) & 1, abort_flag, gerr, 3);
-            ++waited;
-          }
-          if (!ok) break;
+    // ------------------------------------------------------------------ MMA issuer
+    bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 2);
+    const uint32_t b_lo0 = ((smem_u32(S.wimg) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);      // LBO = 512 B
+    const uint32_t a_lbo = ((plane_bytes >> 4) & 0x3FFFu) << 16;
+    // per-tap column offsets in 16-byte units: (PAD + dx*d) pixels, + K-pair (two planes)
+    const uint32_t kp_units = (2 * plane_bytes) >> 4;
+    uint32_t lbase = 0, oseq = 0, waited = 0;      // waited = number of row loads known to have landed
+    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+      Item it;
+      if (!sched.get(idx, it)) continue;
+      for (int j = 0; j < it.rows && ok; ++j) {
+        const long long t_row0 = tr ? clock64() : 0;
+        while (waited < lbase + j + 3 && ok) {
+          ok = mbar_wait(smem_u32(&S.full[waited % NS]), (waited / NS) & 1, abort_flag, gerr, 3);
+          ++waited;
+        }
+        if (!ok) break;
+        uint32_t a_row[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          a_row[t] = ((((slots0 + ((lbase + j + t) % NS) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo) + PAD;
+        for (int s = 0; s < it.nseg && ok; ++s, ++oseq) {
           const uint32_t acc = oseq % NACC;
+          TC_TRACE(1, 0, s == 0 ? t_row0 : clock64());
+          TC_TRACE(1, 1, clock64());
           ok = mbar_wait(smem_u32(&S.tempty[acc]), ((oseq / NACC) & 1) ^ 1, abort_flag, gerr, 4);
           if (!ok) break;
+          TC_TRACE(1, 2, clock64());
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * UMMA_N;
+          if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const uint32_t slot = (lbase + j + 1 + dy) % NS;
-            const uint32_t a_addr = slots0 + slot * SLOT_BYTES + (HALO + dx * d) * 16;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap % 3 - 1;
+              const uint32_t a_lo = a_row[dy] + (uint32_t)(s * SEG + dx * d);
 #pragma unroll
-            for (int kp = 0; kp < 3; ++kp) {
-              const uint64_t adesc = make_desc(a_addr + kp * 2 * PLANE_BYTES, PLANE_BYTES, 128);
-              const uint64_t bdesc = make_desc(wsm + (tap * 3 + kp) * B_TILE_BYTES, 512, 128);
-              umma_tf32(tmem_d, adesc, bdesc, (tap | kp) != 0);
+              for (int kp = 0; kp < 3; ++kp) {
+                umma_tf32(tmem_d, make_desc(a_lo + kp * kp_units, DESC_HI),
+                          make_desc(b_lo0 + (tap * 3 + kp) * (B_TILE_BYTES >> 4), DESC_HI), (tap | kp) != 0);
+              }
+            }
+            umma_commit(smem_u32(&S.tfull[acc]));
+            if (s == it.nseg - 1) {
+              umma_commit(smem_u32(&S.empty[(lbase + j) % NS]));         // top row of this window is done
+              if (j == it.rows - 1) {
+                umma_commit(smem_u32(&S.empty[(lbase + j + 1) % NS]));
+                umma_commit(smem_u32(&S.empty[(lbase + j + 2) % NS]));
+              }
             }
           }
-          umma_commit(smem_u32(&S.tfull[acc]));
-          umma_commit(smem_u32(&S.empty[(lbase + j) % NS]));           // top row of this window is done
-          if (j == it.rows - 1) {
-            umma_commit(smem_u32(&S.empty[(lbase + j + 1) % NS]));
-            umma_commit(smem_u32(&S.empty[(lbase + j + 2) % NS]));
-          }
+          __syncwarp();
+          TC_TRACE(1, 3, clock64());
+          ++tr_n;
         }
-        lbase += it.rows + 2;
       }
+      lbase += it.rows + 2;
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
@@ -252,37 +299,43 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
       Item it;
       if (!sched.get(idx, it)) continue;
-      const int x = it.x0 + quad * 32 + lane;
-      for (int j = 0; j < it.rows && ok; ++j, ++oseq) {
-        const uint32_t acc = oseq % NACC;
-        ok = mbar_wait(smem_u32(&S.tfull[acc]), (oseq / NACC) & 1, abort_flag, gerr, 6);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UMMA_N;
-        uint32_t v[24];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr));
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
-                     : "r"(taddr + 16));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&S.tempty[acc]));
+      for (int j = 0; j < it.rows && ok; ++j) {
         const int y = it.r + (it.q0 + j) * d;
-        if (x < w) {
+        for (int s = 0; s < it.nseg && ok; ++s, ++oseq) {
+          const uint32_t acc = oseq % NACC;
+          if (warp == 2) TC_TRACE(2, 0, clock64());
+          ok = mbar_wait(smem_u32(&S.tfull[acc]), (oseq / NACC) & 1, abort_flag, gerr, 6);
+          if (!ok) break;
+          if (warp == 2) TC_TRACE(2, 1, clock64());
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UMMA_N;
+          uint32_t v[24];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                       : "r"(taddr));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
+                       : "r"(taddr + 16));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&S.tempty[acc]));
+          const int x = it.x0 + s * SEG + quad * 32 + lane;
+          if (x < w) {
+            float4* o_px = out + act_index(it.n, 0, y, x, h, w, PAD);
 #pragma unroll
-          for (int g = 0; g < UBD_NG; ++g) {
-            float4 o;
-            o.x = fmaxf(__uint_as_float(v[4 * g + 0]) + bias[4 * g + 0], 0.f);
-            o.y = fmaxf(__uint_as_float(v[4 * g + 1]) + bias[4 * g + 1], 0.f);
-            o.z = fmaxf(__uint_as_float(v[4 * g + 2]) + bias[4 * g + 2], 0.f);
-            o.w = fmaxf(__uint_as_float(v[4 * g + 3]) + bias[4 * g + 3], 0.f);
-            if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            out[act_index(it.n, g, y, x, h, w)] = o;
+            for (int g = 0; g < UBD_NG; ++g) {
+              float4 o;
+              o.x = fmaxf(__uint_as_float(v[4 * g + 0]) + bias[4 * g + 0], 0.f);
+              o.y = fmaxf(__uint_as_float(v[4 * g + 1]) + bias[4 * g + 1], 0.f);
+              o.z = fmaxf(__uint_as_float(v[4 * g + 2]) + bias[4 * g + 2], 0.f);
+              o.w = fmaxf(__uint_as_float(v[4 * g + 3]) + bias[4 * g + 3], 0.f);
+              if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+              o_px[(size_t)g * wp] = o;
+            }
           }
+          if (warp == 2) { TC_TRACE(2, 2, clock64()); ++tr_n; }
         }
       }
     }
@@ -356,11 +409,13 @@ static int tc_launch_dilconv(ubd_handle h, const float4* in, float4* out, int la
   const uint8_t* base = (const uint8_t*)h->tc_weights.p;
   const uint8_t* wb = base + (size_t)layer * tc::WB_BYTES;
   const uint8_t* zeros = base + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
-  const int n_strips = (ww + tc::TW - 1) / tc::TW;
+  const int sw = ww <= tc::SEG ? tc::SEG : tc::MAX_SW;
+  const int n_strips = (ww + sw - 1) / sw;
   const int n_chunks = ((hh + d - 1) / d + tc::RQ - 1) / tc::RQ;
   const long long items = (long long)n * n_strips * d * n_chunks;
   const int grid = (int)std::min<long long>(items, h->n_sm);
-  tc::dilconv_tf32_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>(in, out, wb, zeros, n, hh, ww, d, round_out, tc_err_flag(h));
+  tc::dilconv_tf32_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>(in, out, wb, zeros, n, hh, ww, d, sw, round_out, tc_err_flag(h),
+                                                                            (long long*)h->tc_trace.p);
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
