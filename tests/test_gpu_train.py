@@ -1,0 +1,164 @@
+"""-m gpu: loss, backward and optimizer of the training step (config E) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import loss as L
+from oracle import net as onet
+from ubdvss_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(**kw):
+    from ubdvss_b200.engine import Engine
+    return Engine(**kw)
+
+
+def _loss_case(n=2, h=24, w=40, n_classes=0, seed=0, scale=3.0):
+    rng = np.random.default_rng(seed)
+    y_true = synth.synth_targets(n, h, w, n_classes, seed)
+    y_pred = rng.normal(0, scale, size=(n, h, w, 1 + n_classes)).astype(np.float32)
+    return y_true, y_pred
+
+
+def _check_loss(y_true, y_pred, n_classes):
+    eng = _engine(n_classes=n_classes)
+    parts, dl = eng.loss(y_pred, y_true)
+    ref_loss, ref_parts, ref_grad = L.loss_and_grad(y_true, y_pred, n_classes > 0)
+    assert abs(parts[0] - ref_loss) <= 2e-5 * max(1.0, abs(ref_loss)), (parts, ref_loss, ref_parts)
+    assert abs(parts[1] - ref_parts["positive"]) <= 2e-5 * max(1.0, ref_parts["positive"])
+    assert abs(parts[2] - ref_parts["negative"]) <= 2e-5 * max(1.0, ref_parts["negative"])
+    assert abs(parts[3] - ref_parts["hard_negative"]) <= 2e-5 * max(1.0, ref_parts["hard_negative"])
+    assert int(parts[5]) == ref_parts["k"]
+    if n_classes:
+        assert abs(parts[4] - ref_parts["classification"]) <= 2e-5 * max(1.0, ref_parts["classification"])
+    assert np.abs(dl - ref_grad).max() <= 1e-7 + 2e-4 * np.abs(ref_grad).max()
+    return parts, dl, ref_grad
+
+
+@pytest.mark.parametrize("n_classes", [0, 4, 26])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_loss_and_gradient_match_oracle(n_classes, seed):
+    y_true, y_pred = _loss_case(n_classes=n_classes, seed=seed)
+    _check_loss(y_true, y_pred, n_classes)
+
+
+def test_loss_edge_cases():
+    y_true, y_pred = _loss_case(seed=5)
+    _check_loss(np.zeros_like(y_true), y_pred, 0)                    # all negative: n_pos clamps, k = 1
+    _check_loss(np.ones_like(y_true), y_pred, 0)                     # all positive: hard = 0
+    z = np.array([[[-20, 20, 0.3, -0.2], [-17, 17, 18, -30]]], np.float32)[..., None]
+    yt = np.zeros((1, 2, 4, 1), np.int32); yt[0, 0, :2] = 1
+    _, dl, _ = _check_loss(yt, z, 0)
+    assert np.all(dl[np.abs(z) >= 17] == 0)                          # clipped BCE kills the gradient
+    # ties at the k-th value: the lower flat indices carry the hard-negative share
+    yt = np.zeros((1, 1, 6, 1), np.int32); yt[0, 0, :2] = 1
+    z = np.array([0.0, 0.0, 1.0, 1.0, 1.0, -1.0], np.float32).reshape(1, 1, 6, 1)
+    _, dl, ref = _check_loss(yt, z, 0)
+    assert dl[0, 0, 2, 0] == dl[0, 0, 3, 0] > dl[0, 0, 4, 0] > 0
+
+
+def test_loss_full_size_config_e():
+    """32 x 128x128 maps (config E per GPU): 524,288 pixels through radix select + ordered ties."""
+    y_true, y_pred = _loss_case(n=32, h=128, w=128, n_classes=0, seed=9, scale=2.0)
+    _check_loss(y_true, y_pred, 0)
+
+
+def _grad_check(n_classes, grey, fml, dtype_u8, shape=(2, 64, 96), seed=3):
+    w = onet.init_weights(n_classes, seed=seed, grey=grey)
+    eng = _engine(grey=grey, fml_compatible=fml, n_classes=n_classes)
+    eng.set_weights(w)
+    n, H, W = shape
+    x = synth.synth_images(n, H, W, seed=seed, channels=1 if grey else 3)
+    y = synth.synth_targets(n, H // 4, W // 4, n_classes, seed=seed)
+    xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
+    if dtype_u8:
+        parts = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    else:
+        parts = eng.train_step(xf, y, _lib.PREPROC_NONE)
+    loss, ref_parts, ref_grads, _ = L.train_step_torch(w, xf, y, n_classes > 0, fml_compatible=fml)
+    assert abs(parts[0] - loss) <= 1e-4 * max(1.0, abs(loss)), (parts, loss)
+    grads = eng.get_grads()
+    for i, (g, r) in enumerate(zip(grads, ref_grads)):
+        assert g.shape == r.shape
+        tol = 1e-6 + 2e-3 * np.abs(r).max()
+        assert np.abs(g - r).max() <= tol, (i, np.abs(g - r).max(), np.abs(r).max())
+    return eng, w, grads
+
+
+@pytest.mark.parametrize("n_classes,grey,fml,u8", [(0, True, True, True), (0, True, True, False), (4, True, True, True),
+                                                  (0, True, False, True), (3, False, True, True)])
+def test_backward_matches_autograd_oracle(n_classes, grey, fml, u8):
+    _grad_check(n_classes, grey, fml, u8)
+
+
+def test_backward_ragged_shape():
+    _grad_check(0, True, True, True, shape=(3, 48, 80), seed=8)
+
+
+def test_adam_step_matches_keras_formula():
+    eng, w, grads = _grad_check(0, True, True, True)
+    params = [a.copy() for a in w]
+    m = [np.zeros_like(a) for a in w]; v = [np.zeros_like(a) for a in w]
+    L.adam_step(params, grads, m, v, t=1, lr=1e-3)
+    eng.adam_step(lr=1e-3)
+    for a, b in zip(eng.get_weights(), params):
+        assert np.abs(a - b).max() <= 1e-7 + 1e-5 * np.abs(b).max()
+    # second step on the updated weights, gradients scaled as after a 2-rank sum all-reduce
+    x = synth.synth_images(2, 64, 96, seed=3)
+    y = synth.synth_targets(2, 16, 24, 0, seed=3)
+    eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    g2 = eng.get_grads()
+    L.adam_step(params, [0.5 * g for g in g2], m, v, t=2, lr=1e-3)
+    eng.adam_step(lr=1e-3, grad_scale=0.5)
+    for a, b in zip(eng.get_weights(), params):
+        assert np.abs(a - b).max() <= 1e-6 + 1e-4 * np.abs(b).max()
+
+
+def test_adam_before_train_step_is_a_state_error():
+    eng = _engine()
+    eng.set_weights(onet.init_weights(0, seed=1))
+    with pytest.raises(_lib.UbdError) as e:
+        eng.adam_step()
+    assert e.value.code == -6
+
+
+def test_keras_shaped_training_loop_reduces_loss():
+    from ubdvss_b200 import losses
+    from ubdvss_b200.net import Adam, B200Model, NetConfig
+    cfg = NetConfig()
+    model = B200Model(cfg, seed=0)
+    model.compile(Adam(2e-3), loss=losses.get_loss(False))
+    x = synth.synth_images(4, 128, 128, seed=2)
+    y = synth.synth_targets(4, 32, 32, 0, seed=2)
+
+    def gen():
+        while True:
+            yield x.astype(np.float32) / 127.5 - 1, y
+    first = model.train_on_batch(x.astype(np.float32) / 127.5 - 1, y)
+    assert model.metrics_names[:4] == ["loss", "positive_loss", "negative_loss", "hard_negative_loss"]
+    model.fit_generator(gen(), steps_per_epoch=15, epochs=2, verbose=0, workers=0)
+    assert model.history["loss"][-1] < 0.8 * first[0]
+    with pytest.raises(RuntimeError):
+        B200Model(cfg, seed=0).train_on_batch(x, y)
+
+
+def test_full_size_config_e_step_is_finite_and_reproducible():
+    """Config E: 32 x 512x512 per GPU.  The oracle is too slow here; check finiteness, determinism and
+    the bias-gradient identity dL/db_head = sum of dL/dlogits."""
+    w = onet.init_weights(0, seed=1234)
+    eng = _engine()
+    eng.set_weights(w)
+    x = np.concatenate([synth.synth_images(8, 512, 512, seed=4)] * 4)
+    y = np.concatenate([synth.synth_targets(8, 128, 128, 0, seed=4)] * 4)
+    p1 = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    g1 = eng.get_grads()
+    p2 = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    g2 = eng.get_grads()
+    assert np.isfinite(p1).all() and np.array_equal(p1, p2)
+    for a, b in zip(g1, g2):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+    logits = eng.forward(x, _lib.PREPROC_MOBILENET)
+    parts, dl = eng.loss(logits, y)
+    assert abs(parts[0] - p1[0]) <= 1e-5 * abs(p1[0])
+    assert abs(g1[22][0] - dl.sum(dtype=np.float64)) <= 1e-4 * max(1.0, np.abs(dl).sum())

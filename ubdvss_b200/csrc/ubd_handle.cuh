@@ -44,6 +44,7 @@ struct ubd_handle_s {
   // training workspaces
   DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss;
   int64_t adam_t = 0;
+  int train_n = 0, train_h = 0, train_w = 0;   // geometry the training maps were last zeroed for
   bool have_grads = false;
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 

@@ -286,10 +286,11 @@ class B200Model:
             pass
         d = _Dev()
         d.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        from .parallel import allreduce_mean_
         t = torch.as_tensor(d, device=f"cuda:{self.device}")
-        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
+        scale = allreduce_mean_(t, self._dist)
         torch.cuda.current_stream(self.device).synchronize()
-        return 1.0 / self._dist.get_world_size()
+        return scale
 
     def train_on_batch(self, x, y, sample_weight=None, class_weight=None, preprocessing=None):
         """One optimizer step; returns ``[loss, positive, negative, hard_negative(, classification)]``."""
