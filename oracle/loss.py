@@ -8,7 +8,8 @@ encoded here are the documented ones:
 
 * ``K.binary_crossentropy(target, output)`` on probabilities (TF backend): clip output to
   [eps, 1-eps] with eps = 1e-7 in float32, ``x = log(p/(1-p))``, then
-  ``sigmoid_cross_entropy_with_logits = max(x,0) - x*t + log1p(exp(-|x|))``.
+  ``sigmoid_cross_entropy_with_logits = max(x,0) - x*t + log1p(exp(-|x|))`` (built with
+  ``tf.where(x >= 0, ...)``, hence differentiable as ``sigmoid(x) - t`` also at x = 0).
 * ``tf.clip_by_value`` passes the gradient where lo <= p <= hi (so saturated logits get 0).
 * ``tf.nn.top_k`` keeps the lower index among equal values.
 * Keras-2 ``Adam``: ``lr_t = lr*sqrt(1-b2^t)/(1-b1^t)``, ``p -= lr_t*m/(sqrt(v)+eps)``, eps=1e-7.
@@ -45,7 +46,13 @@ def loss_torch(y_true, y_pred, classification: bool):
     one = torch.tensor(1.0, dtype=dt)
     pc = torch.clamp(p, eps, one - eps)                                   # K.binary_crossentropy
     x = torch.log(pc / (1 - pc))
-    ce = torch.relu(x) - x * t + torch.log1p(torch.exp(-torch.abs(x)))    # losses.py:97
+    # tf.nn.sigmoid_cross_entropy_with_logits builds relu / -|x| with tf.where(x >= 0, ...), so its
+    # gradient at exactly x = 0 is the smooth sigmoid(x) - t (torch.relu / torch.abs would give a
+    # different sub-gradient there)
+    zeros = torch.zeros_like(x)
+    relu_x = torch.where(x >= 0, x, zeros)
+    neg_abs_x = torch.where(x >= 0, -x, x)
+    ce = relu_x - x * t + torch.log1p(torch.exp(neg_abs_x))                # losses.py:97
     npos = torch.clamp(t.sum(), min=1.0)                                  # losses.py:99
     pos = (ce * t).sum() / npos                                           # losses.py:101
     neg_mask = 1 - t
