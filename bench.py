@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-E training-step measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -233,10 +234,37 @@ def main():
     e2e_s = time.perf_counter() - t0
     n_comp_last = int(counts_h.sum())
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # config E beside it: training step (forward + loss + backward + Adam) on 32 x 512x512 per GPU,
+    # gradients all-reduced over NCCL when N > 1 (the only collective on the path)
+    train_ms = float("nan")
+    train_loss = float("nan")
+    if not args.no_train:
+        from ubdvss_b200 import synth
+        from ubdvss_b200.net import Adam, B200Model, NetConfig
+        from ubdvss_b200 import losses as ulosses
+        eng.set_stream(None)
+        tb = 32
+        tx = np.concatenate([synth.synth_images(8, 512, 512, seed=40 + rank)] * (tb // 8))
+        ty = np.concatenate([synth.synth_targets(8, 128, 128, 0, seed=40 + rank)] * (tb // 8))
+        model = B200Model(NetConfig(), device=local_rank, weights=weights)
+        model.compile(Adam(1e-3), loss=ulosses.get_loss(False))
+        if dist is not None:
+            model.set_distributed(True)
+        for _ in range(2):
+            model.train_on_batch(tx, ty, preprocessing="mobilenet_like")
+        barrier()
+        t0 = time.perf_counter()
+        tsteps = max(2, min(args.steps, 5))
+        for _ in range(tsteps):
+            out = model.train_on_batch(tx, ty, preprocessing="mobilenet_like")
+        torch.cuda.synchronize()
+        train_ms = (time.perf_counter() - t0) * 1e3 / tsteps
+        train_loss = out[0]
+
+    t = torch.tensor([ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, train_ms_max = float(t[0]), float(t[1]), float(t[2])
     total_images = B * world * args.steps
     value = total_images / (ms_max / 1e3)
     e2e_value = total_images / (e2e_ms_max / 1e3)
@@ -267,6 +295,11 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(imgs.nbytes),
                         "d2h_bytes_per_step": int(mask_h.nbytes + 4 * B + 72 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum())}
+        if not args.no_train:
+            line["train_step"] = {"config": "configs[4]: forward + losses.py loss + backward + Adam, batch 32 of 512x512 per GPU, fp32"
+                                            + (", NCCL gradient all-reduce" if world > 1 else ""),
+                                  "ms_per_step": train_ms_max, "images_per_sec": 32 * world / (train_ms_max / 1e3),
+                                  "loss": train_loss}
         if world == 1 and not args.no_cpu_baseline:
             v, step_s, cores = time_cpu(weights, imgs[:args.cpu_sample], thr, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
