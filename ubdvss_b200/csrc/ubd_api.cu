@@ -15,6 +15,7 @@
 #include "ubd_fp32.cuh"
 #include "ubd_handle.cuh"
 #include "ubd_tc.cuh"
+#include "ubd_stem_tc.cuh"
 #include "ubd_train.cuh"
 
 static std::string g_create_error;
@@ -111,6 +112,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   h->n_sm = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return UBD_ERR_CUDA; }
   // preprocessing table for uint8 input: exactly what numpy computes, (v - 127.5) / 127.5 in
   // float64 (net.py:217-218 on a uint8 image) then cast to float32 at the Keras boundary
@@ -139,6 +141,8 @@ extern "C" int ubd_destroy(ubd_handle h) {
   if (h->d_lut) cudaFree(h->d_lut);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   resolve_profile(h);
+  for (cudaEvent_t ev : h->copy_events) cudaEventDestroy(ev);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->own_stream);
   delete h;
   return UBD_OK;
@@ -221,6 +225,7 @@ extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const i
   UBD_CUDA(cudaStreamSynchronize(h->stream));
   h->have_weights = true;
   h->tc_weights_dirty = true;
+  h->stem_weights_dirty = true;
   return UBD_OK;
 }
 
@@ -271,8 +276,6 @@ static int launch_sep(ubd_handle h, const TIn* in, float4* out, int layer, int n
   return UBD_OK;
 }
 
-// TF 'same' stride-2 padding before the image for even sizes is 0; FML pads 1 (net.py:229-232).
-static inline int stride2_pad(ubd_handle h) { return h->fml ? 1 : 0; }
 
 static int run_stem(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W,
                     float4* act1, float4* act2, float4* act3) {
@@ -349,23 +352,41 @@ static int ensure_maps(ubd_handle h, int n, int mh, int mw) {
 }
 
 // d_img: device images.  d_logits (nullable) / d_mask (nullable): device outputs for the whole batch.
+// h_img (nullable): host images; then d_img is the device staging buffer and every chunk is copied on
+// the copy stream just ahead of its compute, so the PCIe transfer of chunk k+1 overlaps chunk k.
 static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
-                          float* d_logits, uint8_t* d_mask, float thr) {
+                          float* d_logits, uint8_t* d_mask, float thr, const void* h_img = nullptr) {
   HostTimer ht_fwd(h, 0);
   const int h4 = H / 4, w4 = W / 4;
   const int chunk = pick_chunk(h, n, H, W);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
-  ENSURE(h->act1, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
+  if (h->precision != UBD_TF32) ENSURE(h->act1, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
   ENSURE(h->act2, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
   { int rc_ = ensure_maps(h, chunk, h4, w4); if (rc_) return rc_; }
   const size_t img_stride = (size_t)H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int cn = std::min(chunk, n - c0);
     const char* img = (const char*)d_img + (size_t)c0 * img_stride;
+    if (h_img) {
+      const size_t k = (size_t)(c0 / chunk);
+      while (h->copy_events.size() <= k) {
+        cudaEvent_t ev;
+        UBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->copy_events.push_back(ev);
+      }
+      UBD_CUDA(cudaMemcpyAsync((void*)img, (const char*)h_img + (size_t)c0 * img_stride, (size_t)cn * img_stride,
+                               cudaMemcpyHostToDevice, h->copy_stream));
+      UBD_CUDA(cudaEventRecord(h->copy_events[k], h->copy_stream));
+      UBD_CUDA(cudaStreamWaitEvent(h->stream, h->copy_events[k], 0));
+    }
     float4* A = (float4*)h->mapA.p;
     float4* B = (float4*)h->mapB.p;
     int rc;
-    { ProfScope ps(h, &h->prof_stem); rc = run_stem(h, img, in_dtype, preproc, cn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, A); }
+    {
+      ProfScope ps(h, &h->prof_stem);
+      if (h->precision == UBD_TF32) rc = run_stem_tc(h, img, in_dtype, preproc, cn, H, W, (float4*)h->act2.p, A);
+      else rc = run_stem(h, img, in_dtype, preproc, cn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, A);
+    }
     if (rc) return rc;
     for (int l = 0; l < UBD_NLAYERS_DIL; ++l) {
       ProfScope ps(h, &h->prof_dil);
@@ -519,8 +540,7 @@ extern "C" int ubd_forward(ubd_handle h, const void* images, int in_dtype, int n
   const size_t lb = (size_t)n * (H / 4) * (W / 4) * h->spec.n_out * sizeof(float);
   ENSURE(h->d_images, ib);
   ENSURE(h->d_logits, lb);
-  UBD_CUDA(cudaMemcpyAsync(h->d_images.p, images, ib, cudaMemcpyHostToDevice, h->stream));
-  rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, nullptr, 0.f);
+  rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, nullptr, 0.f, images);
   if (rc) return rc;
   UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, lb, cudaMemcpyDeviceToHost, h->stream));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
@@ -567,9 +587,8 @@ extern "C" int ubd_segment(ubd_handle h, const void* images, int in_dtype, int n
   ENSURE(h->d_images, ib);
   ENSURE(h->d_mask, q);
   ENSURE(h->d_logits, q * h->spec.n_out * sizeof(float));
-  UBD_CUDA(cudaMemcpyAsync(h->d_images.p, images, ib, cudaMemcpyHostToDevice, h->stream));
   // the mask / logits copies are queued before the component read-back so they overlap it
-  rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, (uint8_t*)h->d_mask.p, logit_thr);
+  rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, (uint8_t*)h->d_mask.p, logit_thr, images);
   if (rc) return rc;
   if (mask_out) UBD_CUDA(cudaMemcpyAsync(mask_out, h->d_mask.p, q, cudaMemcpyDeviceToHost, h->stream));
   if (logits_out) UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, q * h->spec.n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -14,6 +14,8 @@ struct ubd_handle_s {
   WeightSpec spec;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // H2D of chunk k+1 overlaps the compute of chunk k
+  std::vector<cudaEvent_t> copy_events;
   // optional CUDA-event profiling of kernel groups (option "profile")
   bool profile = false;
   struct Prof { double ms = 0; int64_t launches = 0; };
@@ -39,6 +41,8 @@ struct ubd_handle_s {
   int map_h = 0, map_w = 0, map_n = 0;     // shape the padded maps were last zeroed for
   DevBuf outer;
   DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
+  DevBuf stem_wimg;               // pointwise B images of L2 / L3 for the tensor-core stem
+  bool stem_weights_dirty = true;
   DevBuf tc_trace;                // optional event trace of CTA 0 (option "tc_trace")
   DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
   // training workspaces
@@ -50,7 +54,10 @@ struct ubd_handle_s {
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc_trace, &t_acts, &t_grads_act,
+            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc_trace, &stem_wimg, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
   }
 };
+
+// TF 'same' stride-2 padding before the image for even sizes is 0; FML pads 1 (net.py:229-232).
+static inline int stride2_pad(ubd_handle h) { return h->fml ? 1 : 0; }

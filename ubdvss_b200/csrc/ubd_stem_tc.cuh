@@ -1,0 +1,440 @@
+// Fused separable stem for the tensor-core path (net.py:292-296), sm_100a.
+//
+// A separable layer is depthwise 3x3 (216 MAC/px, no reuse across channels -> FP32 pipes) followed by a
+// pointwise 24->24 (576 MAC/px, a dense contraction -> tcgen05).  Both kernels below compute the
+// depthwise output on the FP32 pipes and write it, rounded to tf32, STRAIGHT INTO a shared-memory UMMA
+// A tile ([plane][128 px][16 B], K-major SWIZZLE_NONE, same convention as ubd_tc.cuh); three
+// kind::tf32 MMAs per 128-pixel segment then do the pointwise conv into TMEM, and the epilogue adds
+// bias + ReLU.  The pointwise result never exists as scalar code and the depthwise result never
+// leaves the SM.
+//
+//   stem12_tc_kernel : image -> L1 (separable s2, Cin = 1|3, all FP32, exact) -> L2 depthwise -> L2
+//                      pointwise (tcgen05) -> act2 (half resolution).  The 24-channel L1 map (25 MB per
+//                      1024x1024 image) lives only in shared memory.
+//   stem3_tc_kernel  : act2 -> L3 depthwise s2 -> pointwise (tcgen05) -> act3 (quarter resolution,
+//                      x-padded layout, rounded to the tf32 grid for the dilated tensor-core layers).
+//
+// Tile = 4 rows x 128 px of the layer's output = 4 MMA segments = 4 TMEM accumulators of 32 columns.
+// 256 threads, persistent CTAs; phases of one tile are separated by __syncthreads (generic-proxy
+// writes of the A tile are published to the async proxy with fence.proxy.async).
+#pragma once
+#include "ubd_tc.cuh"
+
+namespace stem {
+
+constexpr int SEGPX = 128;
+constexpr int THREADS = 256;
+constexpr int A_PLANE = SEGPX * 16;           // 2048 B
+constexpr int A_SEG = UBD_NG * A_PLANE;       // 12288 B
+constexpr int PW_IMG_BYTES = 3 * tc::B_TILE_BYTES;      // 3 K-pairs x 1 KB
+constexpr int PW_WB_BYTES = PW_IMG_BYTES + 128;         // + bias[32]
+
+// pointwise weights (1,1,24,24) [c][o] -> UMMA B image, tf32-rounded; then bias
+__global__ void build_pw_img_kernel(const float* __restrict__ params, int64_t pw_off, int64_t b_off, uint8_t* __restrict__ dst_) {
+  float* dst = reinterpret_cast<float*>(dst_);
+  for (int i = threadIdx.x; i < PW_IMG_BYTES / 4; i += blockDim.x) {
+    const int kp = i / 256, rem = i % 256;
+    const int kcore = rem / 128, ngroup = (rem % 128) / 32, row = (rem % 32) / 4, col = rem % 4;
+    const int ic = kp * 8 + kcore * 4 + col, oc = ngroup * 8 + row;
+    dst[i] = oc < UBD_NF ? tc::round_tf32(params[pw_off + ic * UBD_NF + oc]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[PW_IMG_BYTES / 4 + i] = i < UBD_NF ? params[b_off + i] : 0.f;
+}
+
+template <int ROWS>
+struct PwSmem {                                // common head of both kernels' shared memory
+  uint8_t A[ROWS * A_SEG];                     // depthwise output, UMMA A tiles (12 KB per segment)
+  uint8_t wimg[PW_IMG_BYTES];
+  float bias[32];
+  uint64_t mma_bar;
+  uint32_t tmem_base;
+};
+
+// Pointwise conv of the ROWS staged segments: 3 MMAs each, one commit.  Call from warp 0 only.
+template <int ROWS>
+__device__ __forceinline__ void pw_issue(PwSmem<ROWS>& S, uint32_t tmem_base) {
+  if (tc::elect_one()) {
+    const uint32_t a0 = ((tc::smem_u32(S.A) >> 4) & 0x3FFFu) | (((uint32_t)A_PLANE >> 4) << 16);
+    const uint32_t b0 = ((tc::smem_u32(S.wimg) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int kp = 0; kp < 3; ++kp)
+        tc::umma_tf32(tmem_base + r * tc::UMMA_N, tc::make_desc(a0 + ((r * A_SEG + kp * 2 * A_PLANE) >> 4), tc::DESC_HI),
+                      tc::make_desc(b0 + ((kp * tc::B_TILE_BYTES) >> 4), tc::DESC_HI), kp != 0);
+    tc::umma_commit(tc::smem_u32(&S.mma_bar));
+  }
+  __syncwarp();
+}
+
+// Epilogue of one tile: warp w reads TMEM quadrant w&3 of segments (w>>2), (w>>2)+2, ...
+template <bool ROUND, int ROWS>
+__device__ __forceinline__ void pw_epilogue(PwSmem<ROWS>& S, uint32_t tmem_base, float4* __restrict__ out, int n, int y0, int x0,
+                                            int Ho, int Wo, int opad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quad = warp & 3;
+#pragma unroll
+  for (int h = 0; h < ROWS / 2; ++h) {
+    const int r = (warp >> 2) + 2 * h;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * tc::UMMA_N;
+    uint32_t v[24];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
+                 : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int y = y0 + r, x = x0 + quad * 32 + lane;
+    if (y < Ho && x < Wo) {
+#pragma unroll
+      for (int g = 0; g < UBD_NG; ++g) {
+        float4 o;
+        o.x = fmaxf(__uint_as_float(v[4 * g + 0]) + S.bias[4 * g + 0], 0.f);
+        o.y = fmaxf(__uint_as_float(v[4 * g + 1]) + S.bias[4 * g + 1], 0.f);
+        o.z = fmaxf(__uint_as_float(v[4 * g + 2]) + S.bias[4 * g + 2], 0.f);
+        o.w = fmaxf(__uint_as_float(v[4 * g + 3]) + S.bias[4 * g + 3], 0.f);
+        if (ROUND) { o.x = tc::round_tf32(o.x); o.y = tc::round_tf32(o.y); o.z = tc::round_tf32(o.z); o.w = tc::round_tf32(o.w); }
+        out[act_index(n, g, y, x, Ho, Wo, opad)] = o;
+      }
+    }
+  }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void pw_setup(PwSmem<ROWS>& S, const uint8_t* __restrict__ wb, int warp) {
+  constexpr int TMEM_COLS = ROWS * tc::UMMA_N;
+  for (int i = threadIdx.x; i < PW_WB_BYTES / 4; i += blockDim.x)
+    reinterpret_cast<float*>(S.wimg)[i] = __ldg(reinterpret_cast<const float*>(wb) + i);     // wimg then bias
+  if (threadIdx.x == 0) {
+    tc::mbar_init(tc::smem_u32(&S.mma_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // wimg was written through the generic proxy
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+}
+
+// Waits for the tile's MMAs.  Plain (unbounded-by-design but HW-suspending) parity wait; the producer of
+// this barrier is the tcgen05.commit issued a few instructions earlier by this same CTA.
+template <int ROWS>
+__device__ __forceinline__ void wait_mma(PwSmem<ROWS>& S, uint32_t parity, int* gerr) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(tc::smem_u32(&S.mma_bar)), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > 1500000000LL) { atomicCAS(gerr, 0, 7); break; }
+  }
+  tc::tc_fence_after();
+}
+
+// ------------------------------------------------------------------------------------------------
+// image -> L1 -> L2 (act2).  CIN = 1 or 3; TIn = uint8_t (lut or plain cast) or float.
+// Tile = 2 rows x 128 px of act2 (two segments) so that two CTAs fit one SM and overlap each other's
+// phases.  The image patch is staged RAW with aligned 16-byte loads (one round of memory latency).
+// ------------------------------------------------------------------------------------------------
+constexpr int R12 = 2;                         // act2 rows per tile
+constexpr int A1_ROWS = R12 + 2;               // L1 rows feeding them
+constexpr int A1_COLS = SEGPX + 2;             // 130
+constexpr int A1_PITCH = 132;                  // float4 per (row, plane)
+constexpr int IMG_ROWS = 2 * A1_ROWS + 1;      // 9
+constexpr int IMG_COLS = 2 * A1_COLS + 1;      // 261
+
+constexpr int IMG_HALF = 132;                  // floats per (row, parity): columns 2k / 2k+1 of the patch
+
+template <int CIN, typename TIn>
+struct Smem12 {
+  PwSmem<R12> pw;
+  float4 act1[A1_ROWS * UBD_NG * A1_PITCH];    // 50688 B
+  float imgE[CIN][IMG_ROWS * IMG_HALF];        // preprocessed patch, even columns
+  float imgO[CIN][IMG_ROWS * IMG_HALF];        // odd columns (a stride-2 tap walk is then conflict-free)
+  __align__(16) float pw1[CIN * UBD_NF];
+  __align__(16) float b1[UBD_NF];
+  __align__(16) float dw2[9 * UBD_NF];
+  float dw1[9 * CIN], lut[256];
+};
+
+template <int CIN, typename TIn>
+__global__ void __launch_bounds__(THREADS, 2)
+stem12_tc_kernel(const TIn* __restrict__ img, float4* __restrict__ act2, const float* __restrict__ params,
+                 int64_t off_dw1, int64_t off_pw1, int64_t off_b1, int64_t off_dw2, const uint8_t* __restrict__ wb2,
+                 const float* __restrict__ lut, float pre_scale, float pre_shift,
+                 int N, int H, int W, int pad_t, int pad_l, int* gerr) {
+  using SM = Smem12<CIN, TIn>;
+  constexpr int ELT = (int)sizeof(TIn);
+  constexpr int EPC = 16 / ELT;                                   // elements per 16-byte chunk
+  constexpr int CHUNKS = (IMG_COLS * CIN * ELT + 15) / 16 + 1;    // chunks covering one patch row
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int H2 = H / 2, W2 = W / 2;
+  for (int i = threadIdx.x; i < 9 * CIN; i += THREADS) S.dw1[i] = params[off_dw1 + i];
+  for (int i = threadIdx.x; i < CIN * UBD_NF; i += THREADS) S.pw1[i] = params[off_pw1 + i];
+  for (int i = threadIdx.x; i < UBD_NF; i += THREADS) S.b1[i] = params[off_b1 + i];
+  for (int i = threadIdx.x; i < 9 * UBD_NF; i += THREADS) S.dw2[i] = params[off_dw2 + i];
+  if (lut) for (int i = threadIdx.x; i < 256; i += THREADS) S.lut[i] = lut[i];
+  pw_setup(S.pw, wb2, warp);
+  const uint32_t tmem_base = S.pw.tmem_base;
+  const long long row_bytes_img = (long long)W * CIN * ELT;      // multiple of 16 (W % 16 == 0)
+  float dw1r[9 * CIN];
+#pragma unroll
+  for (int i = 0; i < 9 * CIN; ++i) dw1r[i] = S.dw1[i];
+
+  const int xt = (W2 + SEGPX - 1) / SEGPX, yt = (H2 + R12 - 1) / R12;
+  const int ntiles = N * yt * xt;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int x0 = (tile % xt) * SEGPX, y0 = ((tile / xt) % yt) * R12, n = tile / (xt * yt);
+    // ---- phase 1: image patch with aligned 16-byte loads (one round of latency), preprocessed and
+    //      split into even / odd columns.  A chunk is entirely inside or outside the image row (rows
+    //      are 16-byte multiples); outside = 0 AFTER preprocessing (the layers' zero padding).
+    const int iy0 = 2 * (y0 - 1) - pad_t, ix0 = 2 * (x0 - 1) - pad_l;
+    const int b0 = ix0 * CIN * ELT;                                   // byte offset of patch column 0 in the image row
+    const int a0 = b0 >= 0 ? (b0 & ~15) : -(((-b0) + 15) & ~15);      // floored to 16
+    const int e0 = (a0 - b0) / ELT;                                   // patch element index of chunk 0, element 0 (<= 0)
+    const uint8_t* img_n = reinterpret_cast<const uint8_t*>(img) + (size_t)n * H * row_bytes_img;
+    for (int i = threadIdx.x; i < IMG_ROWS * CHUNKS; i += THREADS) {
+      const int r = i / CHUNKS, c = i - r * CHUNKS;
+      const int iy = iy0 + r;
+      const int off = a0 + 16 * c;
+      const bool inside = iy >= 0 && iy < H && off >= 0 && off < (int)row_bytes_img;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (inside) v = __ldg(reinterpret_cast<const uint4*>(img_n + (size_t)iy * row_bytes_img + off));
+      const TIn* e = reinterpret_cast<const TIn*>(&v);
+      const int idx0 = e0 + c * EPC;
+      float* rowE[CIN]; float* rowO[CIN];
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) { rowE[ch] = &S.imgE[ch][r * IMG_HALF]; rowO[ch] = &S.imgO[ch][r * IMG_HALF]; }
+#pragma unroll
+      for (int k = 0; k < EPC; ++k) {
+        const int idx = idx0 + k;
+        if ((unsigned)idx >= (unsigned)(IMG_COLS * CIN)) continue;
+        const int col = CIN == 1 ? idx : idx / CIN, ch = CIN == 1 ? 0 : idx - col * CIN;
+        float f = 0.f;
+        if (inside) {
+          if constexpr (sizeof(TIn) == 1) f = lut ? S.lut[(int)e[k]] : (float)e[k];
+          else { f = (float)e[k]; if (pre_scale != 0.f) f = (f - pre_shift) / pre_scale; }
+        }
+        float* dst = (col & 1) ? rowO[CIN == 1 ? 0 : ch] : rowE[CIN == 1 ? 0 : ch];
+        dst[col >> 1] = f;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: L1 (depthwise + pointwise + bias + ReLU, FP32) into shared memory; positions
+    //      outside the L1 map are ZERO (they are L2's 'same' padding, not relu(bias))
+    for (int i = threadIdx.x; i < A1_ROWS * A1_COLS; i += THREADS) {
+      const int r = i / A1_COLS, c = i % A1_COLS;
+      const int yy = y0 - 1 + r, xx = x0 - 1 + c;
+      float4 o[UBD_NG];
+      if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) {
+        float d[CIN];
+#pragma unroll
+        for (int ch = 0; ch < CIN; ++ch) {
+          float a = 0.f;
+#pragma unroll
+          for (int ti = 0; ti < 3; ++ti) {
+            const float* E = &S.imgE[ch][(2 * r + ti) * IMG_HALF + c];
+            const float* O = &S.imgO[ch][(2 * r + ti) * IMG_HALF + c];
+            a = fmaf(E[0], dw1r[(ti * 3 + 0) * CIN + ch], a);       // patch column 2c
+            a = fmaf(O[0], dw1r[(ti * 3 + 1) * CIN + ch], a);       // 2c + 1
+            a = fmaf(E[1], dw1r[(ti * 3 + 2) * CIN + ch], a);       // 2c + 2
+          }
+          d[ch] = a;
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(S.b1);
+        const float4* p4 = reinterpret_cast<const float4*>(S.pw1);
+#pragma unroll
+        for (int g = 0; g < UBD_NG; ++g) {
+          float4 a = b4[g];
+#pragma unroll
+          for (int ch = 0; ch < CIN; ++ch) {
+            const float4 w = p4[ch * UBD_NG + g];
+            a.x = fmaf(d[ch], w.x, a.x); a.y = fmaf(d[ch], w.y, a.y); a.z = fmaf(d[ch], w.z, a.z); a.w = fmaf(d[ch], w.w, a.w);
+          }
+          o[g] = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < UBD_NG; ++g) o[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int g = 0; g < UBD_NG; ++g) S.act1[(r * UBD_NG + g) * A1_PITCH + c] = o[g];
+    }
+    __syncthreads();
+    // ---- phase 3: L2 depthwise -> A tiles.  Task = (plane, pixel column): both output rows from a
+    //      4-row x 3-column window; consecutive threads read consecutive float4 (conflict-free).
+    for (int task = threadIdx.x; task < UBD_NG * SEGPX; task += THREADS) {
+      const int p = task % SEGPX, g = task / SEGPX;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+      const float4* w4 = reinterpret_cast<const float4*>(S.dw2) + g;       // [tap][6 planes]
+#pragma unroll
+      for (int rr = 0; rr < A1_ROWS; ++rr) {
+        const float4* row = &S.act1[(rr * UBD_NG + g) * A1_PITCH + p];
+        const float4 in0 = row[0], in1 = row[1], in2 = row[2];
+        if (rr < 3) {                                                       // tap row rr of output row 0
+          const float4 wa = w4[(rr * 3 + 0) * UBD_NG], wb = w4[(rr * 3 + 1) * UBD_NG], wc = w4[(rr * 3 + 2) * UBD_NG];
+          acc0.x = fmaf(in0.x, wa.x, fmaf(in1.x, wb.x, fmaf(in2.x, wc.x, acc0.x)));
+          acc0.y = fmaf(in0.y, wa.y, fmaf(in1.y, wb.y, fmaf(in2.y, wc.y, acc0.y)));
+          acc0.z = fmaf(in0.z, wa.z, fmaf(in1.z, wb.z, fmaf(in2.z, wc.z, acc0.z)));
+          acc0.w = fmaf(in0.w, wa.w, fmaf(in1.w, wb.w, fmaf(in2.w, wc.w, acc0.w)));
+        }
+        if (rr >= 1) {                                                      // tap row rr-1 of output row 1
+          const float4 wa = w4[((rr - 1) * 3 + 0) * UBD_NG], wb = w4[((rr - 1) * 3 + 1) * UBD_NG], wc = w4[((rr - 1) * 3 + 2) * UBD_NG];
+          acc1.x = fmaf(in0.x, wa.x, fmaf(in1.x, wb.x, fmaf(in2.x, wc.x, acc1.x)));
+          acc1.y = fmaf(in0.y, wa.y, fmaf(in1.y, wb.y, fmaf(in2.y, wc.y, acc1.y)));
+          acc1.z = fmaf(in0.z, wa.z, fmaf(in1.z, wb.z, fmaf(in2.z, wc.z, acc1.z)));
+          acc1.w = fmaf(in0.w, wa.w, fmaf(in1.w, wb.w, fmaf(in2.w, wc.w, acc1.w)));
+        }
+      }
+      reinterpret_cast<float4*>(S.pw.A + 0 * A_SEG + g * A_PLANE)[p] =
+          make_float4(tc::round_tf32(acc0.x), tc::round_tf32(acc0.y), tc::round_tf32(acc0.z), tc::round_tf32(acc0.w));
+      reinterpret_cast<float4*>(S.pw.A + 1 * A_SEG + g * A_PLANE)[p] =
+          make_float4(tc::round_tf32(acc1.x), tc::round_tf32(acc1.y), tc::round_tf32(acc1.z), tc::round_tf32(acc1.w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- phase 4: pointwise conv on the tensor core, epilogue
+    if (warp == 0) pw_issue(S.pw, tmem_base);
+    wait_mma(S.pw, it & 1, gerr);
+    pw_epilogue<false>(S.pw, tmem_base, act2, n, y0, x0, H2, W2, 0);
+    tc::tc_fence_before();
+    __syncthreads();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(R12 * tc::UMMA_N) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// act2 -> L3 (act3, quarter resolution, padded layout, tf32 grid)
+// ------------------------------------------------------------------------------------------------
+constexpr int R3 = 4;                          // act3 rows per tile
+struct Smem3 {
+  PwSmem<R3> pw;
+  float dw3[9 * UBD_NF];
+};
+
+__global__ void __launch_bounds__(THREADS, 3)
+stem3_tc_kernel(const float4* __restrict__ act2, float4* __restrict__ act3, const float* __restrict__ params,
+                int64_t off_dw3, const uint8_t* __restrict__ wb3, int N, int H2, int W2, int pad_t, int pad_l, int* gerr) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
+  Smem3& S = *reinterpret_cast<Smem3*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int H4 = H2 / 2, W4 = W2 / 2;
+  for (int i = threadIdx.x; i < 9 * UBD_NF; i += THREADS) S.dw3[i] = params[off_dw3 + i];
+  pw_setup(S.pw, wb3, warp);
+  const uint32_t tmem_base = S.pw.tmem_base;
+  const int xt = (W4 + SEGPX - 1) / SEGPX, yt = (H4 + R3 - 1) / R3;
+  const int ntiles = N * yt * xt;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int x0 = (tile % xt) * SEGPX, y0 = ((tile / xt) % yt) * R3, n = tile / (xt * yt);
+    // depthwise stride 2 straight from the act2 map (L1/L2-cached) into the A tiles
+    for (int task = threadIdx.x; task < R3 * UBD_NG * SEGPX; task += THREADS) {
+      const int p = task % SEGPX, g = (task / SEGPX) % UBD_NG, r = task / (SEGPX * UBD_NG);
+      const int y = y0 + r, x = x0 + p;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y < H4 && x < W4) {
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti) {
+          const int iy = 2 * y + ti - pad_t;
+          if (iy < 0 || iy >= H2) continue;
+#pragma unroll
+          for (int tj = 0; tj < 3; ++tj) {
+            const int ix = 2 * x + tj - pad_l;
+            if (ix < 0 || ix >= W2) continue;
+            const float4 v = __ldg(&act2[act_index(n, g, iy, ix, H2, W2, 0)]);
+            const float* wk = &S.dw3[(ti * 3 + tj) * UBD_NF + 4 * g];
+            a.x = fmaf(v.x, wk[0], a.x); a.y = fmaf(v.y, wk[1], a.y); a.z = fmaf(v.z, wk[2], a.z); a.w = fmaf(v.w, wk[3], a.w);
+          }
+        }
+      }
+      reinterpret_cast<float4*>(S.pw.A + r * A_SEG + g * A_PLANE)[p] =
+          make_float4(tc::round_tf32(a.x), tc::round_tf32(a.y), tc::round_tf32(a.z), tc::round_tf32(a.w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) pw_issue(S.pw, tmem_base);
+    wait_mma(S.pw, it & 1, gerr);
+    pw_epilogue<true>(S.pw, tmem_base, act3, n, y0, x0, H4, W4, UBD_MAP_PAD);
+    tc::tc_fence_before();
+    __syncthreads();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(R3 * tc::UMMA_N) : "memory");
+}
+
+}  // namespace stem
+
+template <int CIN, typename TIn>
+static int stem12_launch(ubd_handle h, const TIn* img, float4* act2, const float* lut, float ps, float psh,
+                         int n, int H, int W, int p2) {
+  auto kern = stem::stem12_tc_kernel<CIN, TIn>;
+  const size_t smem = sizeof(stem::Smem12<CIN, TIn>) + 128;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  const int ntiles = n * ((H / 2 + stem::R12 - 1) / stem::R12) * ((W / 2 + stem::SEGPX - 1) / stem::SEGPX);
+  const int grid = std::min(ntiles, 2 * h->n_sm);
+  const uint8_t* wb2 = (const uint8_t*)h->stem_wimg.p;
+  kern<<<grid, stem::THREADS, smem, h->stream>>>(img, act2, h->d_params, h->spec.off[0], h->spec.off[1], h->spec.off[2],
+                                                 h->spec.off[3], wb2, lut, ps, psh, n, H, W, p2, p2, tc_err_flag(h));
+  ++h->launches;
+  UBD_CUDA(cudaGetLastError());
+  return UBD_OK;
+}
+
+// tensor-core stem: image -> act3.  Needs tc_prepare (error flag) and the pointwise B images.
+static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W,
+                       float4* act2, float4* act3) {
+  int rc = tc_prepare(h);
+  if (rc) return rc;
+  if (!h->stem_wimg.p) {
+    UBD_CUDA(cudaMalloc(&h->stem_wimg.p, 2 * stem::PW_WB_BYTES));
+    h->stem_wimg.cap = 2 * stem::PW_WB_BYTES;
+    h->stem_weights_dirty = true;
+  }
+  if (h->stem_weights_dirty) {
+    for (int l = 1; l <= 2; ++l) {
+      stem::build_pw_img_kernel<<<1, 256, 0, h->stream>>>(h->d_params, h->spec.off[3 * l + 1], h->spec.off[3 * l + 2],
+                                                          (uint8_t*)h->stem_wimg.p + (l - 1) * stem::PW_WB_BYTES);
+      ++h->launches;
+    }
+    UBD_CUDA(cudaGetLastError());
+    h->stem_weights_dirty = false;
+  }
+  const int p2 = stride2_pad(h);
+  const bool mob = preproc == UBD_PREPROC_MOBILENET;
+  if (h->spec.cin == 1) {
+    if (in_dtype == UBD_U8) rc = stem12_launch<1, uint8_t>(h, (const uint8_t*)d_img, act2, mob ? h->d_lut : nullptr, 0.f, 0.f, n, H, W, p2);
+    else rc = stem12_launch<1, float>(h, (const float*)d_img, act2, nullptr, mob ? 127.5f : 0.f, 127.5f, n, H, W, p2);
+  } else {
+    if (in_dtype == UBD_U8) rc = stem12_launch<3, uint8_t>(h, (const uint8_t*)d_img, act2, mob ? h->d_lut : nullptr, 0.f, 0.f, n, H, W, p2);
+    else rc = stem12_launch<3, float>(h, (const float*)d_img, act2, nullptr, mob ? 127.5f : 0.f, 127.5f, n, H, W, p2);
+  }
+  if (rc) return rc;
+  {
+    static bool attr_set = false;
+    const size_t smem = sizeof(stem::Smem3) + 128;
+    if (!attr_set) { cudaFuncSetAttribute(stem::stem3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const int H2 = H / 2, W2 = W / 2;
+    const int ntiles = n * ((H2 / 2 + stem::R3 - 1) / stem::R3) * ((W2 / 2 + stem::SEGPX - 1) / stem::SEGPX);
+    const int grid = std::min(ntiles, 3 * h->n_sm);
+    stem::stem3_tc_kernel<<<grid, stem::THREADS, smem, h->stream>>>(act2, act3, h->d_params, h->spec.off[6],
+                                                                    (const uint8_t*)h->stem_wimg.p + stem::PW_WB_BYTES,
+                                                                    n, H2, W2, p2, p2, tc_err_flag(h));
+    ++h->launches;
+    UBD_CUDA(cudaGetLastError());
+  }
+  return UBD_OK;
+}

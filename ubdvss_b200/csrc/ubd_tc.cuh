@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, const uint8_t* __restrict__ wb,
                     const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int round_out, int* gerr,
                     long long* trace) {
-  extern __shared__ uint8_t smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform
   const int lane = threadIdx.x & 31;
   volatile int* abort_flag = &S.abort_flag;
