@@ -324,15 +324,21 @@ static int launch_head(ubd_handle h, const float4* in, float* logits, uint8_t* m
   return UBD_OK;
 }
 
+// Images per sweep of the dilated layers / head ("chunk") and per stem launch ("stem chunk").
+// Measured on B200 (64 x 1024x1024, tf32), six dilated layers: chunk 16 -> 1.49 ms, 32 -> 1.20 ms,
+// 64 -> 1.11 ms: per-launch fixed cost and the tail of the static item schedule outweigh L2 residency
+// of the ping-pong maps, so the dilated layers take up to 64 images at once (bounded by ~1 GB of maps).
+// The stem runs in sub-chunks of 16 so that the H2D copy of sub-chunk k+1 overlaps the stem of k.
 static int pick_chunk(ubd_handle h, int n, int H, int W) {
   if (h->opt_chunk > 0) return std::min(n, h->opt_chunk);
-  // Images per sweep through the layer stack.  Measured on B200 (1024x1024 inputs, tf32): 2 -> 4.56 ms,
-  // 4 -> 2.33, 8 -> 2.00, 16 -> 1.82 ms for the six dilated layers of a 64-image batch: the per-launch
-  // fixed cost and the tail of the static item schedule outweigh L2 residency of the ping-pong maps,
-  // so take 16 images (more for small maps), bounded by ~1.6 GB of half-resolution stem scratch.
-  const double per_img = (double)(H / 4) * (W / 4) * 2.0 * 96.0;
-  int c = (int)(100e6 / per_img);
-  return std::max(1, std::min(n, std::max(c, 16)));
+  const double per_img = (double)(H / 4) * (W / 4 + 2 * UBD_MAP_PAD) * 2.0 * 96.0;
+  const int c = (int)(1.0e9 / per_img);
+  return std::max(1, std::min(n, std::min(std::max(c, 16), 64)));
+}
+static int pick_stem_chunk(ubd_handle h, int chunk, int H, int W) {
+  const double per_img = (double)(H / 2) * (W / 2) * 96.0;        // one half-resolution map
+  const int c = (int)(0.5e9 / per_img);
+  return std::max(1, std::min(chunk, std::min(std::max(c, 1), 16)));
 }
 
 // The two ping-pong quarter-resolution maps.  Their zero x-padding is the convolution's zero padding,
@@ -359,35 +365,42 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
   HostTimer ht_fwd(h, 0);
   const int h4 = H / 4, w4 = W / 4;
   const int chunk = pick_chunk(h, n, H, W);
+  const int schunk = pick_stem_chunk(h, chunk, H, W);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
-  if (h->precision != UBD_TF32) ENSURE(h->act1, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
-  ENSURE(h->act2, (size_t)chunk * UBD_NG * half_px * sizeof(float4));
+  if (h->precision != UBD_TF32) ENSURE(h->act1, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
+  ENSURE(h->act2, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
   { int rc_ = ensure_maps(h, chunk, h4, w4); if (rc_) return rc_; }
   const size_t img_stride = (size_t)H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
+  const size_t map_img = act_elems(1, h4, w4, UBD_MAP_PAD);
+  size_t copy_k = 0;
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int cn = std::min(chunk, n - c0);
-    const char* img = (const char*)d_img + (size_t)c0 * img_stride;
-    if (h_img) {
-      const size_t k = (size_t)(c0 / chunk);
-      while (h->copy_events.size() <= k) {
-        cudaEvent_t ev;
-        UBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        h->copy_events.push_back(ev);
-      }
-      UBD_CUDA(cudaMemcpyAsync((void*)img, (const char*)h_img + (size_t)c0 * img_stride, (size_t)cn * img_stride,
-                               cudaMemcpyHostToDevice, h->copy_stream));
-      UBD_CUDA(cudaEventRecord(h->copy_events[k], h->copy_stream));
-      UBD_CUDA(cudaStreamWaitEvent(h->stream, h->copy_events[k], 0));
-    }
     float4* A = (float4*)h->mapA.p;
     float4* B = (float4*)h->mapB.p;
     int rc;
-    {
+    // ---- stem, sub-chunk by sub-chunk, each right behind its H2D copy
+    for (int s0 = 0; s0 < cn; s0 += schunk) {
+      const int sn = std::min(schunk, cn - s0);
+      const char* img = (const char*)d_img + (size_t)(c0 + s0) * img_stride;
+      if (h_img) {
+        while (h->copy_events.size() <= copy_k) {
+          cudaEvent_t ev;
+          UBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          h->copy_events.push_back(ev);
+        }
+        UBD_CUDA(cudaMemcpyAsync((void*)img, (const char*)h_img + (size_t)(c0 + s0) * img_stride, (size_t)sn * img_stride,
+                                 cudaMemcpyHostToDevice, h->copy_stream));
+        UBD_CUDA(cudaEventRecord(h->copy_events[copy_k], h->copy_stream));
+        UBD_CUDA(cudaStreamWaitEvent(h->stream, h->copy_events[copy_k], 0));
+        ++copy_k;
+      }
       ProfScope ps(h, &h->prof_stem);
-      if (h->precision == UBD_TF32) rc = run_stem_tc(h, img, in_dtype, preproc, cn, H, W, (float4*)h->act2.p, A);
-      else rc = run_stem(h, img, in_dtype, preproc, cn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, A);
+      float4* a3 = A + (size_t)s0 * map_img;
+      if (h->precision == UBD_TF32) rc = run_stem_tc(h, img, in_dtype, preproc, sn, H, W, (float4*)h->act2.p, a3);
+      else rc = run_stem(h, img, in_dtype, preproc, sn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, a3);
+      if (rc) return rc;
     }
-    if (rc) return rc;
+    // ---- dilated layers and head over the whole chunk
     for (int l = 0; l < UBD_NLAYERS_DIL; ++l) {
       ProfScope ps(h, &h->prof_dil);
       const float* w = h->d_params + h->spec.off[9 + 2 * l];

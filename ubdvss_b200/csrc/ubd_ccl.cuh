@@ -70,19 +70,21 @@ ccl_merge1_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, in
   const int p = y * w + x;
   const bool c = m[p] != 0;
   const bool hasW = x > 0, hasN = y > 0, hasE = x < w - 1;
+  // A vertical link is needed only at the first pixel of a run overlap: if W and NW are of my class and
+  // in my warp segment, then p~W and NW~N are implicit run links (ccl_init_kernel) and W~NW is W's job.
+  const bool seg0 = (x & 31) == 0;
   if (c) {
-    // decision tree: a present N neighbour already touches W, NW and NE, so one link suffices;
-    // W links inside a warp segment are implicit in ccl_init_kernel.
+    // decision tree: a present N neighbour already touches W, NW and NE, so one link suffices
     if (hasN && m[p - w] != 0) {
-      uf_union(par, p, p - w);
+      if (seg0 || m[p - 1] == 0 || m[p - w - 1] == 0) uf_union(par, p, p - w);
     } else {
       if (hasN && hasE && m[p - w + 1] != 0) uf_union(par, p, p - w + 1);
       if (hasN && hasW && m[p - w - 1] != 0) uf_union(par, p, p - w - 1);
-      else if (hasW && (x & 31) == 0 && m[p - 1] != 0) uf_union(par, p, p - 1);
+      else if (hasW && seg0 && m[p - 1] != 0) uf_union(par, p, p - 1);
     }
   } else {
-    if (hasN && m[p - w] == 0) uf_union(par, p, p - w);
-    if (hasW && (x & 31) == 0 && m[p - 1] == 0) uf_union(par, p, p - 1);
+    if (hasN && m[p - w] == 0 && (seg0 || m[p - 1] != 0 || m[p - w - 1] != 0)) uf_union(par, p, p - w);
+    if (hasW && seg0 && m[p - 1] == 0) uf_union(par, p, p - 1);
   }
 }
 

@@ -22,10 +22,14 @@
 // warp-uniform; only the asynchronous instruction itself sits under elect.sync, so descriptors live
 // in uniform registers and an MMA costs a handful of issue slots:
 //   warp 0   : producer  - bulk copies into the slot ring      (empty[] -> full[])
-//   warp 1   : MMA issue - 27 tcgen05.mma per segment into a TMEM accumulator, tcgen05.commit to
-//              tmem_full[] and to the empty[] of the row that is no longer needed
+//   warps 1,6: MMA issue - even / odd segments: 27 tcgen05.mma per segment into a TMEM accumulator,
+//              tcgen05.commit to tmem_full[].  Two issuers because the issue of one segment blocks on
+//              the operand feed (~47 cycles / MMA) and each barrier wait costs ~230 cycles: while one
+//              warp waits, the other keeps the tensor pipe fed (measured with the in-kernel trace).
 //   warps 2-5: epilogue  - tcgen05.ld (lane = pixel, 24 columns = channels), bias + ReLU,
-//              six coalesced float4 stores (one per plane)
+//              six coalesced float4 stores (one per plane); warp 2 also releases the staged rows: once
+//              it has seen tmem_full of a row's last segment every MMA that read the top row of that
+//              window has completed, whichever warp issued it.
 #pragma once
 #include "ubd_handle.cuh"
 
@@ -45,7 +49,7 @@ constexpr int B_TILE_BYTES = UMMA_N * 8 * 4;  // 1024: [2 K cores][4 oc groups][
 constexpr int W_BYTES = N_MMA * B_TILE_BYTES; // 27648
 constexpr int WB_BYTES = W_BYTES + 128;       // + bias[24] padded to 32 floats
 constexpr int RQ = 8;                         // output rows per work item
-constexpr int THREADS = 192;
+constexpr int THREADS = 224;                  // producer, MMA issuer A, 4 epilogue warps, MMA issuer B
 constexpr int ZERO_BYTES = MAX_SLOT_BYTES;
 
 struct Smem {
@@ -230,8 +234,9 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
         ++tr_n;
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 6) {
+    // ------------------------------------------------------------------ MMA issuers (even / odd segments)
+    const uint32_t parity = warp == 6 ? 1u : 0u;
     bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 2);
     const uint32_t b_lo0 = ((smem_u32(S.wimg) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);      // LBO = 512 B
     const uint32_t a_lbo = ((plane_bytes >> 4) & 0x3FFFu) << 16;
@@ -242,25 +247,25 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
       Item it;
       if (!sched.get(idx, it)) continue;
       for (int j = 0; j < it.rows && ok; ++j) {
-        const long long t_row0 = tr ? clock64() : 0;
-        while (waited < lbase + j + 3 && ok) {
-          ok = mbar_wait(smem_u32(&S.full[waited % NS]), (waited / NS) & 1, abort_flag, gerr, 3);
-          ++waited;
-        }
-        if (!ok) break;
-        uint32_t a_row[3];
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-          a_row[t] = ((((slots0 + ((lbase + j + t) % NS) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo) + PAD;
         for (int s = 0; s < it.nseg && ok; ++s, ++oseq) {
+          if ((oseq & 1u) != parity) continue;
+          if (parity == 0) TC_TRACE(1, 0, clock64());
+          while (waited < lbase + j + 3 && ok) {
+            ok = mbar_wait(smem_u32(&S.full[waited % NS]), (waited / NS) & 1, abort_flag, gerr, 3);
+            ++waited;
+          }
+          if (!ok) break;
+          if (parity == 0) TC_TRACE(1, 1, clock64());
           const uint32_t acc = oseq % NACC;
-          TC_TRACE(1, 0, s == 0 ? t_row0 : clock64());
-          TC_TRACE(1, 1, clock64());
           ok = mbar_wait(smem_u32(&S.tempty[acc]), ((oseq / NACC) & 1) ^ 1, abort_flag, gerr, 4);
           if (!ok) break;
-          TC_TRACE(1, 2, clock64());
+          if (parity == 0) TC_TRACE(1, 2, clock64());
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * UMMA_N;
+          uint32_t a_row[3];
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            a_row[t] = ((((slots0 + ((lbase + j + t) % NS) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo) + PAD;
           if (elect_one()) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -273,17 +278,9 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
               }
             }
             umma_commit(smem_u32(&S.tfull[acc]));
-            if (s == it.nseg - 1) {
-              umma_commit(smem_u32(&S.empty[(lbase + j) % NS]));         // top row of this window is done
-              if (j == it.rows - 1) {
-                umma_commit(smem_u32(&S.empty[(lbase + j + 1) % NS]));
-                umma_commit(smem_u32(&S.empty[(lbase + j + 2) % NS]));
-              }
-            }
           }
           __syncwarp();
-          TC_TRACE(1, 3, clock64());
-          ++tr_n;
+          if (parity == 0) { TC_TRACE(1, 3, clock64()); ++tr_n; }
         }
       }
       lbase += it.rows + 2;
@@ -295,10 +292,13 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
     float bias[UBD_NF];
 #pragma unroll
     for (int c = 0; c < UBD_NF; ++c) bias[c] = ok ? S.bias[c] : 0.f;
-    uint32_t oseq = 0;
-    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+    uint32_t it_rows_plus2 = 0;
+    uint32_t oseq = 0, lbase = 0;
+    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x, lbase += it_rows_plus2) {
       Item it;
+      it_rows_plus2 = 0;
       if (!sched.get(idx, it)) continue;
+      it_rows_plus2 = it.rows + 2;
       for (int j = 0; j < it.rows && ok; ++j) {
         const int y = it.r + (it.q0 + j) * d;
         for (int s = 0; s < it.nseg && ok; ++s, ++oseq) {
@@ -307,6 +307,15 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
           ok = mbar_wait(smem_u32(&S.tfull[acc]), (oseq / NACC) & 1, abort_flag, gerr, 6);
           if (!ok) break;
           if (warp == 2) TC_TRACE(2, 1, clock64());
+          if (warp == 2 && lane == 0 && s == it.nseg - 1) {
+            // every MMA of output rows <= j of this item has completed: the top row of the window
+            // (and, after the item's last row, the two rows below it) can be overwritten
+            mbar_arrive(smem_u32(&S.empty[(lbase + j) % NS]));
+            if (j == it.rows - 1) {
+              mbar_arrive(smem_u32(&S.empty[(lbase + j + 1) % NS]));
+              mbar_arrive(smem_u32(&S.empty[(lbase + j + 2) % NS]));
+            }
+          }
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UMMA_N;
           uint32_t v[24];
