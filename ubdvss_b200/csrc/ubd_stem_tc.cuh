@@ -139,29 +139,35 @@ __device__ __forceinline__ void wait_mma(PwSmem<ROWS>& S, uint32_t parity, int* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// image -> L1 -> L2 (act2).  CIN = 1 or 3; TIn = uint8_t (lut or plain cast) or float.
-// Tile = 2 rows x 128 px of act2 (two segments) so that two CTAs fit one SM and overlap each other's
-// phases.  The image patch is staged RAW with aligned 16-byte loads (one round of memory latency).
+// image -> L1 -> L2 (act2), streaming.  CIN = 1 or 3; TIn = uint8_t (lut or plain cast) or float.
+//
+// A CTA takes work items (image, 128-px column strip, RS act2 rows) from an atomic counter and walks
+// the strip top to bottom two act2 rows at a time.  Every image row is loaded and preprocessed once
+// (even / odd column arrays so the stride-2 taps are conflict-free), every L1 row is computed once
+// into a 4-row ring in shared memory, the L2 depthwise of a row pair is written as two UMMA A
+// segments, 6 MMAs do the pointwise conv, the epilogue of the pair overlaps the next pair's L1 work.
+// Two __syncthreads per row pair; two CTAs per SM hide each other's barrier and MMA latency.
 // ------------------------------------------------------------------------------------------------
-constexpr int R12 = 2;                         // act2 rows per tile
-constexpr int A1_ROWS = R12 + 2;               // L1 rows feeding them
-constexpr int A1_COLS = SEGPX + 2;             // 130
+constexpr int R12 = 2;                         // act2 rows per MMA batch (two segments)
+constexpr int RS = 16;                         // act2 rows per work item
+constexpr int A1_COLS = SEGPX + 2;             // 130 L1 columns feed 128 L2 columns
 constexpr int A1_PITCH = 132;                  // float4 per (row, plane)
-constexpr int IMG_ROWS = 2 * A1_ROWS + 1;      // 9
-constexpr int IMG_COLS = 2 * A1_COLS + 1;      // 261
-
-constexpr int IMG_HALF = 132;                  // floats per (row, parity): columns 2k / 2k+1 of the patch
+constexpr int A1_RING = 4;                     // L1 rows resident (power of two)
+constexpr int IMG_COLS = 2 * A1_COLS + 1;      // 261 image columns feed 130 L1 columns
+constexpr int IMG_HALF = 132;                  // floats per (row, parity)
+constexpr int IMG_RING = 16;                   // image rows resident (power of two)
 
 template <int CIN, typename TIn>
 struct Smem12 {
   PwSmem<R12> pw;
-  float4 act1[A1_ROWS * UBD_NG * A1_PITCH];    // 50688 B
-  float imgE[CIN][IMG_ROWS * IMG_HALF];        // preprocessed patch, even columns
-  float imgO[CIN][IMG_ROWS * IMG_HALF];        // odd columns (a stride-2 tap walk is then conflict-free)
+  float4 act1[A1_RING * UBD_NG * A1_PITCH];    // 50688 B
+  float imgE[CIN][IMG_RING * IMG_HALF];        // preprocessed image rows, even patch columns
+  float imgO[CIN][IMG_RING * IMG_HALF];        // odd patch columns
   __align__(16) float pw1[CIN * UBD_NF];
   __align__(16) float b1[UBD_NF];
   __align__(16) float dw2[9 * UBD_NF];
   float dw1[9 * CIN], lut[256];
+  int item;
 };
 
 template <int CIN, typename TIn>
@@ -169,144 +175,200 @@ __global__ void __launch_bounds__(THREADS, 2)
 stem12_tc_kernel(const TIn* __restrict__ img, float4* __restrict__ act2, const float* __restrict__ params,
                  int64_t off_dw1, int64_t off_pw1, int64_t off_b1, int64_t off_dw2, const uint8_t* __restrict__ wb2,
                  const float* __restrict__ lut, float pre_scale, float pre_shift,
-                 int N, int H, int W, int pad_t, int pad_l, int* gerr) {
+                 int N, int H, int W, int pad_t, int pad_l, int* __restrict__ work_counter, int* gerr) {
   using SM = Smem12<CIN, TIn>;
   constexpr int ELT = (int)sizeof(TIn);
-  constexpr int EPC = 16 / ELT;                                   // elements per 16-byte chunk
-  constexpr int CHUNKS = (IMG_COLS * CIN * ELT + 15) / 16 + 1;    // chunks covering one patch row
+  constexpr int EPQ = 4 / ELT;                                    // elements per 4-byte load (4 for u8, 1 for float)
+  constexpr int QUADS = (IMG_COLS * CIN * ELT + 3) / 4 + 1;       // 4-byte words covering one patch row
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
   SM& S = *reinterpret_cast<SM*>(smem_raw);
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
   const int H2 = H / 2, W2 = W / 2;
-  for (int i = threadIdx.x; i < 9 * CIN; i += THREADS) S.dw1[i] = params[off_dw1 + i];
-  for (int i = threadIdx.x; i < CIN * UBD_NF; i += THREADS) S.pw1[i] = params[off_pw1 + i];
-  for (int i = threadIdx.x; i < UBD_NF; i += THREADS) S.b1[i] = params[off_b1 + i];
-  for (int i = threadIdx.x; i < 9 * UBD_NF; i += THREADS) S.dw2[i] = params[off_dw2 + i];
-  if (lut) for (int i = threadIdx.x; i < 256; i += THREADS) S.lut[i] = lut[i];
+  for (int i = tid; i < 9 * CIN; i += THREADS) S.dw1[i] = params[off_dw1 + i];
+  for (int i = tid; i < CIN * UBD_NF; i += THREADS) S.pw1[i] = params[off_pw1 + i];
+  for (int i = tid; i < UBD_NF; i += THREADS) S.b1[i] = params[off_b1 + i];
+  for (int i = tid; i < 9 * UBD_NF; i += THREADS) S.dw2[i] = params[off_dw2 + i];
+  if (lut) for (int i = tid; i < 256; i += THREADS) S.lut[i] = lut[i];
   pw_setup(S.pw, wb2, warp);
   const uint32_t tmem_base = S.pw.tmem_base;
-  const long long row_bytes_img = (long long)W * CIN * ELT;      // multiple of 16 (W % 16 == 0)
+  const int row_bytes_img = W * CIN * ELT;                        // multiple of 16
   float dw1r[9 * CIN];
 #pragma unroll
   for (int i = 0; i < 9 * CIN; ++i) dw1r[i] = S.dw1[i];
 
-  const int xt = (W2 + SEGPX - 1) / SEGPX, yt = (H2 + R12 - 1) / R12;
-  const int ntiles = N * yt * xt;
-  uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int x0 = (tile % xt) * SEGPX, y0 = ((tile / xt) % yt) * R12, n = tile / (xt * yt);
-    // ---- phase 1: image patch with aligned 16-byte loads (one round of latency), preprocessed and
-    //      split into even / odd columns.  A chunk is entirely inside or outside the image row (rows
-    //      are 16-byte multiples); outside = 0 AFTER preprocessing (the layers' zero padding).
-    const int iy0 = 2 * (y0 - 1) - pad_t, ix0 = 2 * (x0 - 1) - pad_l;
-    const int b0 = ix0 * CIN * ELT;                                   // byte offset of patch column 0 in the image row
-    const int a0 = b0 >= 0 ? (b0 & ~15) : -(((-b0) + 15) & ~15);      // floored to 16
-    const int e0 = (a0 - b0) / ELT;                                   // patch element index of chunk 0, element 0 (<= 0)
-    const uint8_t* img_n = reinterpret_cast<const uint8_t*>(img) + (size_t)n * H * row_bytes_img;
-    for (int i = threadIdx.x; i < IMG_ROWS * CHUNKS; i += THREADS) {
-      const int r = i / CHUNKS, c = i - r * CHUNKS;
-      const int iy = iy0 + r;
-      const int off = a0 + 16 * c;
-      const bool inside = iy >= 0 && iy < H && off >= 0 && off < (int)row_bytes_img;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (inside) v = __ldg(reinterpret_cast<const uint4*>(img_n + (size_t)iy * row_bytes_img + off));
-      const TIn* e = reinterpret_cast<const TIn*>(&v);
-      const int idx0 = e0 + c * EPC;
-      float* rowE[CIN]; float* rowO[CIN];
+  const int xt = (W2 + SEGPX - 1) / SEGPX, yt = (H2 + RS - 1) / RS;
+  const int nitems = N * yt * xt;
+  uint32_t mma_count = 0;                                        // MMA batches issued by this CTA (barrier parity)
+
+  // image row `iy` (may be outside the image) -> ring slot; words [q0, q0 + nq) of the patch row
+  auto load_word = [&](const uint8_t* img_n, int iy, int a0, int q) -> uint32_t {
+    const int off = a0 + 4 * q;
+    if (iy < 0 || iy >= H || off < 0 || off >= row_bytes_img) return 0u;
+    return __ldg(reinterpret_cast<const uint32_t*>(img_n + (size_t)iy * row_bytes_img + off));
+  };
+  auto store_word = [&](uint32_t v, int iy, int a0, int e0, int q) {
+    const int off = a0 + 4 * q;
+    const bool inside = iy >= 0 && iy < H && off >= 0 && off < row_bytes_img;
+    const int slot = iy & (IMG_RING - 1);
+    const TIn* e = reinterpret_cast<const TIn*>(&v);
 #pragma unroll
-      for (int ch = 0; ch < CIN; ++ch) { rowE[ch] = &S.imgE[ch][r * IMG_HALF]; rowO[ch] = &S.imgO[ch][r * IMG_HALF]; }
-#pragma unroll
-      for (int k = 0; k < EPC; ++k) {
-        const int idx = idx0 + k;
-        if ((unsigned)idx >= (unsigned)(IMG_COLS * CIN)) continue;
-        const int col = CIN == 1 ? idx : idx / CIN, ch = CIN == 1 ? 0 : idx - col * CIN;
-        float f = 0.f;
-        if (inside) {
-          if constexpr (sizeof(TIn) == 1) f = lut ? S.lut[(int)e[k]] : (float)e[k];
-          else { f = (float)e[k]; if (pre_scale != 0.f) f = (f - pre_shift) / pre_scale; }
-        }
-        float* dst = (col & 1) ? rowO[CIN == 1 ? 0 : ch] : rowE[CIN == 1 ? 0 : ch];
-        dst[col >> 1] = f;
+    for (int k = 0; k < EPQ; ++k) {
+      const int idx = e0 + q * EPQ + k;
+      if ((unsigned)idx >= (unsigned)(IMG_COLS * CIN)) continue;
+      const int col = CIN == 1 ? idx : idx / CIN, ch = CIN == 1 ? 0 : idx - col * CIN;
+      float f = 0.f;
+      if (inside) {
+        if constexpr (sizeof(TIn) == 1) f = lut ? S.lut[(int)e[k]] : (float)e[k];
+        else { f = (float)e[k]; if (pre_scale != 0.f) f = (f - pre_shift) / pre_scale; }
       }
+      ((col & 1) ? S.imgO[ch] : S.imgE[ch])[slot * IMG_HALF + (col >> 1)] = f;
     }
-    __syncthreads();
-    // ---- phase 2: L1 (depthwise + pointwise + bias + ReLU, FP32) into shared memory; positions
-    //      outside the L1 map are ZERO (they are L2's 'same' padding, not relu(bias))
-    for (int i = threadIdx.x; i < A1_ROWS * A1_COLS; i += THREADS) {
-      const int r = i / A1_COLS, c = i % A1_COLS;
-      const int yy = y0 - 1 + r, xx = x0 - 1 + c;
-      float4 o[UBD_NG];
-      if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) {
-        float d[CIN];
+  };
+  // one L1 pixel (row yy, tile column c) -> ring.  Outside the L1 map: zero (L2's 'same' padding).
+  auto l1_pixel = [&](int yy, int c, int x0) {
+    const int xx = x0 - 1 + c;
+    float4 o[UBD_NG];
+    if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) {
+      float d[CIN];
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        float a = 0.f;
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti) {
+          const int slot = (2 * yy - pad_t + ti) & (IMG_RING - 1);
+          const float* E = &S.imgE[ch][slot * IMG_HALF + c];
+          const float* O = &S.imgO[ch][slot * IMG_HALF + c];
+          a = fmaf(E[0], dw1r[(ti * 3 + 0) * CIN + ch], a);
+          a = fmaf(O[0], dw1r[(ti * 3 + 1) * CIN + ch], a);
+          a = fmaf(E[1], dw1r[(ti * 3 + 2) * CIN + ch], a);
+        }
+        d[ch] = a;
+      }
+      const float4* b4 = reinterpret_cast<const float4*>(S.b1);
+      const float4* p4 = reinterpret_cast<const float4*>(S.pw1);
+#pragma unroll
+      for (int g = 0; g < UBD_NG; ++g) {
+        float4 a = b4[g];
 #pragma unroll
         for (int ch = 0; ch < CIN; ++ch) {
-          float a = 0.f;
-#pragma unroll
-          for (int ti = 0; ti < 3; ++ti) {
-            const float* E = &S.imgE[ch][(2 * r + ti) * IMG_HALF + c];
-            const float* O = &S.imgO[ch][(2 * r + ti) * IMG_HALF + c];
-            a = fmaf(E[0], dw1r[(ti * 3 + 0) * CIN + ch], a);       // patch column 2c
-            a = fmaf(O[0], dw1r[(ti * 3 + 1) * CIN + ch], a);       // 2c + 1
-            a = fmaf(E[1], dw1r[(ti * 3 + 2) * CIN + ch], a);       // 2c + 2
-          }
-          d[ch] = a;
+          const float4 w = p4[ch * UBD_NG + g];
+          a.x = fmaf(d[ch], w.x, a.x); a.y = fmaf(d[ch], w.y, a.y); a.z = fmaf(d[ch], w.z, a.z); a.w = fmaf(d[ch], w.w, a.w);
         }
-        const float4* b4 = reinterpret_cast<const float4*>(S.b1);
-        const float4* p4 = reinterpret_cast<const float4*>(S.pw1);
-#pragma unroll
-        for (int g = 0; g < UBD_NG; ++g) {
-          float4 a = b4[g];
-#pragma unroll
-          for (int ch = 0; ch < CIN; ++ch) {
-            const float4 w = p4[ch * UBD_NG + g];
-            a.x = fmaf(d[ch], w.x, a.x); a.y = fmaf(d[ch], w.y, a.y); a.z = fmaf(d[ch], w.z, a.z); a.w = fmaf(d[ch], w.w, a.w);
-          }
-          o[g] = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-        }
-      } else {
-#pragma unroll
-        for (int g = 0; g < UBD_NG; ++g) o[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        o[g] = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
       }
+    } else {
 #pragma unroll
-      for (int g = 0; g < UBD_NG; ++g) S.act1[(r * UBD_NG + g) * A1_PITCH + c] = o[g];
+      for (int g = 0; g < UBD_NG; ++g) o[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int rs = yy & (A1_RING - 1);
+#pragma unroll
+    for (int g = 0; g < UBD_NG; ++g) S.act1[(rs * UBD_NG + g) * A1_PITCH + c] = o[g];
+  };
+
+  while (true) {
+    if (tid == 0) S.item = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int item = S.item;
+    if (item >= nitems) break;
+    const int x0 = (item % xt) * SEGPX, y0 = ((item / xt) % yt) * RS, n = item / (xt * yt);
+    const int npairs = min(RS, H2 - y0) / 2;
+    const uint8_t* img_n = reinterpret_cast<const uint8_t*>(img) + (size_t)n * H * row_bytes_img;
+    const int ix0 = 2 * (x0 - 1) - pad_l;
+    const int b0 = ix0 * CIN * ELT;
+    const int a0 = b0 >= 0 ? (b0 & ~3) : -(((-b0) + 3) & ~3);       // floored to 4 bytes
+    const int e0 = (a0 - b0) / ELT;                                 // patch element index of word 0 (<= 0)
+    // ---- prologue: image rows for L1 rows y0-1 .. y0+4, then L1 rows y0-1 .. y0+2
+    const int iyA = 2 * (y0 - 1) - pad_t;                           // first image row needed
+    for (int i = tid; i < 13 * QUADS; i += THREADS) {
+      const int r = i / QUADS, q = i - r * QUADS;
+      store_word(load_word(img_n, iyA + r, a0, q), iyA + r, a0, e0, q);
     }
     __syncthreads();
-    // ---- phase 3: L2 depthwise -> A tiles.  Task = (plane, pixel column): both output rows from a
-    //      4-row x 3-column window; consecutive threads read consecutive float4 (conflict-free).
-    for (int task = threadIdx.x; task < UBD_NG * SEGPX; task += THREADS) {
-      const int p = task % SEGPX, g = task / SEGPX;
-      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-      const float4* w4 = reinterpret_cast<const float4*>(S.dw2) + g;       // [tap][6 planes]
+    for (int i = tid; i < 4 * A1_COLS; i += THREADS) l1_pixel(y0 - 1 + i / A1_COLS, i % A1_COLS, x0);
+    __syncthreads();
+
+    for (int p = 0; p < npairs; ++p) {
+      const int y = y0 + 2 * p;                                     // act2 rows y, y+1 this iteration
+      // (a) issue the loads of the 4 image rows that L1 rows y+5, y+6 add (used next iteration)
+      const int iyN = 2 * (y + 5) - pad_t + 1;
+      constexpr bool PREFETCH = 4 * QUADS <= 2 * THREADS;          // grey uint8: two words per thread in flight
+      uint32_t w0 = 0u, w1 = 0u;
+      const int i0 = tid, i1 = tid + THREADS;
+      if (PREFETCH && p + 1 < npairs) {
+        w0 = load_word(img_n, iyN + i0 / QUADS, a0, i0 % QUADS);
+        if (i1 < 4 * QUADS) w1 = load_word(img_n, iyN + i1 / QUADS, a0, i1 % QUADS);
+      }
+      // (c) previous pair: its MMAs are done by now -> epilogue; also frees the A tiles
+      if (p > 0) {
+        wait_mma(S.pw, (mma_count - 1) & 1, gerr);
+        pw_epilogue<false>(S.pw, tmem_base, act2, n, y - 2, x0, H2, W2, 0);
+        tc::tc_fence_before();
+      }
+      // (d) L2 depthwise of rows y, y+1 -> A segments 0, 1.  Task = (plane, pixel column).
+      {
+        const int px = tid & (SEGPX - 1), gb = (tid >> 7) * 3;
+        int rs[4];
 #pragma unroll
-      for (int rr = 0; rr < A1_ROWS; ++rr) {
-        const float4* row = &S.act1[(rr * UBD_NG + g) * A1_PITCH + p];
-        const float4 in0 = row[0], in1 = row[1], in2 = row[2];
-        if (rr < 3) {                                                       // tap row rr of output row 0
-          const float4 wa = w4[(rr * 3 + 0) * UBD_NG], wb = w4[(rr * 3 + 1) * UBD_NG], wc = w4[(rr * 3 + 2) * UBD_NG];
-          acc0.x = fmaf(in0.x, wa.x, fmaf(in1.x, wb.x, fmaf(in2.x, wc.x, acc0.x)));
-          acc0.y = fmaf(in0.y, wa.y, fmaf(in1.y, wb.y, fmaf(in2.y, wc.y, acc0.y)));
-          acc0.z = fmaf(in0.z, wa.z, fmaf(in1.z, wb.z, fmaf(in2.z, wc.z, acc0.z)));
-          acc0.w = fmaf(in0.w, wa.w, fmaf(in1.w, wb.w, fmaf(in2.w, wc.w, acc0.w)));
-        }
-        if (rr >= 1) {                                                      // tap row rr-1 of output row 1
-          const float4 wa = w4[((rr - 1) * 3 + 0) * UBD_NG], wb = w4[((rr - 1) * 3 + 1) * UBD_NG], wc = w4[((rr - 1) * 3 + 2) * UBD_NG];
-          acc1.x = fmaf(in0.x, wa.x, fmaf(in1.x, wb.x, fmaf(in2.x, wc.x, acc1.x)));
-          acc1.y = fmaf(in0.y, wa.y, fmaf(in1.y, wb.y, fmaf(in2.y, wc.y, acc1.y)));
-          acc1.z = fmaf(in0.z, wa.z, fmaf(in1.z, wb.z, fmaf(in2.z, wc.z, acc1.z)));
-          acc1.w = fmaf(in0.w, wa.w, fmaf(in1.w, wb.w, fmaf(in2.w, wc.w, acc1.w)));
+        for (int rr = 0; rr < 4; ++rr) rs[rr] = (y - 1 + rr) & (A1_RING - 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int g = gb + k;
+          const float4* w4 = reinterpret_cast<const float4*>(S.dw2) + g;       // [tap][6 planes]
+          float4 wt[9];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) wt[t] = w4[t * UBD_NG];
+          float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const float4* row = &S.act1[(rs[rr] * UBD_NG + g) * A1_PITCH + px];
+            const float4 in0 = row[0], in1 = row[1], in2 = row[2];
+            if (rr < 3) {
+              const float4 wa = wt[rr * 3], wb = wt[rr * 3 + 1], wc = wt[rr * 3 + 2];
+              acc0.x = fmaf(in0.x, wa.x, fmaf(in1.x, wb.x, fmaf(in2.x, wc.x, acc0.x)));
+              acc0.y = fmaf(in0.y, wa.y, fmaf(in1.y, wb.y, fmaf(in2.y, wc.y, acc0.y)));
+              acc0.z = fmaf(in0.z, wa.z, fmaf(in1.z, wb.z, fmaf(in2.z, wc.z, acc0.z)));
+              acc0.w = fmaf(in0.w, wa.w, fmaf(in1.w, wb.w, fmaf(in2.w, wc.w, acc0.w)));
+            }
+            if (rr >= 1) {
+              const float4 wa = wt[(rr - 1) * 3], wb = wt[(rr - 1) * 3 + 1], wc = wt[(rr - 1) * 3 + 2];
+              acc1.x = fmaf(in0.x, wa.x, fmaf(in1.x, wb.x, fmaf(in2.x, wc.x, acc1.x)));
+              acc1.y = fmaf(in0.y, wa.y, fmaf(in1.y, wb.y, fmaf(in2.y, wc.y, acc1.y)));
+              acc1.z = fmaf(in0.z, wa.z, fmaf(in1.z, wb.z, fmaf(in2.z, wc.z, acc1.z)));
+              acc1.w = fmaf(in0.w, wa.w, fmaf(in1.w, wb.w, fmaf(in2.w, wc.w, acc1.w)));
+            }
+          }
+          reinterpret_cast<float4*>(S.pw.A + 0 * A_SEG + g * A_PLANE)[px] =
+              make_float4(tc::round_tf32(acc0.x), tc::round_tf32(acc0.y), tc::round_tf32(acc0.z), tc::round_tf32(acc0.w));
+          reinterpret_cast<float4*>(S.pw.A + 1 * A_SEG + g * A_PLANE)[px] =
+              make_float4(tc::round_tf32(acc1.x), tc::round_tf32(acc1.y), tc::round_tf32(acc1.z), tc::round_tf32(acc1.w));
         }
       }
-      reinterpret_cast<float4*>(S.pw.A + 0 * A_SEG + g * A_PLANE)[p] =
-          make_float4(tc::round_tf32(acc0.x), tc::round_tf32(acc0.y), tc::round_tf32(acc0.z), tc::round_tf32(acc0.w));
-      reinterpret_cast<float4*>(S.pw.A + 1 * A_SEG + g * A_PLANE)[p] =
-          make_float4(tc::round_tf32(acc1.x), tc::round_tf32(acc1.y), tc::round_tf32(acc1.z), tc::round_tf32(acc1.w));
+      // (e) the image words loaded in (a) have arrived: preprocess into the ring
+      if (p + 1 < npairs) {
+        if (PREFETCH) {
+          store_word(w0, iyN + i0 / QUADS, a0, e0, i0 % QUADS);
+          if (i1 < 4 * QUADS) store_word(w1, iyN + i1 / QUADS, a0, e0, i1 % QUADS);
+        } else {
+          for (int i = tid; i < 4 * QUADS; i += THREADS)
+            store_word(load_word(img_n, iyN + i / QUADS, a0, i % QUADS), iyN + i / QUADS, a0, e0, i % QUADS);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      tc::tc_fence_after();
+      if (warp == 0) pw_issue(S.pw, tmem_base);
+      ++mma_count;
+      // (b) L1 rows y+3, y+4 for the next iteration, into the ring slots of rows y-1, y (free since the
+      //     barrier above); runs while the tensor core does this pair's pointwise conv
+      if (p + 1 < npairs) {
+        l1_pixel(y + 3 + tid / A1_COLS, tid % A1_COLS, x0);
+        if (tid < 2 * A1_COLS - THREADS) l1_pixel(y + 3 + (tid + THREADS) / A1_COLS, (tid + THREADS) % A1_COLS, x0);
+        __syncthreads();
+      }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    // ---- phase 4: pointwise conv on the tensor core, epilogue
-    if (warp == 0) pw_issue(S.pw, tmem_base);
-    wait_mma(S.pw, it & 1, gerr);
-    pw_epilogue<false>(S.pw, tmem_base, act2, n, y0, x0, H2, W2, 0);
+    // ---- last pair of the item
+    wait_mma(S.pw, (mma_count - 1) & 1, gerr);
+    pw_epilogue<false>(S.pw, tmem_base, act2, n, y0 + 2 * (npairs - 1), x0, H2, W2, 0);
     tc::tc_fence_before();
     __syncthreads();
   }
@@ -383,12 +445,18 @@ static int stem12_launch(ubd_handle h, const TIn* img, float4* act2, const float
   auto kern = stem::stem12_tc_kernel<CIN, TIn>;
   const size_t smem = sizeof(stem::Smem12<CIN, TIn>) + 128;
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  const int ntiles = n * ((H / 2 + stem::R12 - 1) / stem::R12) * ((W / 2 + stem::SEGPX - 1) / stem::SEGPX);
-  const int grid = std::min(ntiles, 2 * h->n_sm);
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // 2 CTAs / SM
+    attr_set = true;
+  }
+  const int nitems = n * ((H / 2 + stem::RS - 1) / stem::RS) * ((W / 2 + stem::SEGPX - 1) / stem::SEGPX);
+  const int grid = std::min(nitems, 2 * h->n_sm);
   const uint8_t* wb2 = (const uint8_t*)h->stem_wimg.p;
+  int* counter = reinterpret_cast<int*>((uint8_t*)h->stem_wimg.p + 2 * stem::PW_WB_BYTES);
+  UBD_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
   kern<<<grid, stem::THREADS, smem, h->stream>>>(img, act2, h->d_params, h->spec.off[0], h->spec.off[1], h->spec.off[2],
-                                                 h->spec.off[3], wb2, lut, ps, psh, n, H, W, p2, p2, tc_err_flag(h));
+                                                 h->spec.off[3], wb2, lut, ps, psh, n, H, W, p2, p2, counter, tc_err_flag(h));
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
@@ -400,8 +468,8 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
   int rc = tc_prepare(h);
   if (rc) return rc;
   if (!h->stem_wimg.p) {
-    UBD_CUDA(cudaMalloc(&h->stem_wimg.p, 2 * stem::PW_WB_BYTES));
-    h->stem_wimg.cap = 2 * stem::PW_WB_BYTES;
+    UBD_CUDA(cudaMalloc(&h->stem_wimg.p, 2 * stem::PW_WB_BYTES + 64));       // + work counter
+    h->stem_wimg.cap = 2 * stem::PW_WB_BYTES + 64;
     h->stem_weights_dirty = true;
   }
   if (h->stem_weights_dirty) {
@@ -426,7 +494,11 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
   {
     static bool attr_set = false;
     const size_t smem = sizeof(stem::Smem3) + 128;
-    if (!attr_set) { cudaFuncSetAttribute(stem::stem3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (!attr_set) {
+      cudaFuncSetAttribute(stem::stem3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(stem::stem3_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_set = true;
+    }
     const int H2 = H / 2, W2 = W / 2;
     const int ntiles = n * ((H2 / 2 + stem::R3 - 1) / stem::R3) * ((W2 / 2 + stem::SEGPX - 1) / stem::SEGPX);
     const int grid = std::min(ntiles, 3 * h->n_sm);
