@@ -51,35 +51,43 @@ def test_config_a_parity(precision):
     _check(eng, w, xf, _lib.PREPROC_NONE, precision=precision)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("fml", [True, False])
 @pytest.mark.parametrize("n_classes,grey", [(0, True), (6, True), (26, True), (3, False)])
-def test_variants(fml, n_classes, grey):
+def test_variants(fml, n_classes, grey, precision):
     w = onet.init_weights(n_classes, seed=5, grey=grey)
-    eng = _engine(grey=grey, fml_compatible=fml, n_classes=n_classes)
+    eng = _engine(grey=grey, fml_compatible=fml, n_classes=n_classes, precision=precision)
     eng.set_weights(w)
     x = synth.synth_images(3, 64, 192, seed=2, channels=1 if grey else 3)
-    got, ref = _check(eng, w, x, _lib.PREPROC_MOBILENET, fml=fml)
+    got, ref = _check(eng, w, x, _lib.PREPROC_MOBILENET, fml=fml, precision=precision)
     assert got.shape == (3, 16, 48, 1 + n_classes)
-    assert np.abs(got - ref).max() <= 1e-4
+    assert np.abs(got - ref).max() <= (1e-4 if precision == "fp32" else 2e-2)
+    # float input = already preprocessed (Keras semantics), and raw uint8 without preprocessing
+    xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
+    got_f = eng.forward(xf, _lib.PREPROC_NONE)
+    assert np.abs(got_f - got).max() <= 1e-5
+    _check(eng, w, x, _lib.PREPROC_NONE, fml=fml, precision=precision)
 
 
-def test_ragged_and_large_shapes():
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_ragged_and_large_shapes(precision):
     """Non-square, sides that are multiples of 16 but not of 64, and the 2176x3840 scan (config C)."""
     w = onet.init_weights(0, seed=9)
-    eng = _engine()
+    eng = _engine(precision=precision)
     eng.set_weights(w)
-    for shape in [(1, 16, 16), (2, 48, 80), (1, 144, 400)]:
+    for shape in [(1, 16, 16), (2, 48, 80), (1, 144, 400), (2, 272, 1040)]:
         x = synth.synth_images(shape[0], shape[1], shape[2], seed=4)
-        _check(eng, w, x, _lib.PREPROC_NONE)
-    x = synth.synth_images(1, 2176, 3840, seed=5)
-    _check(eng, w, x, _lib.PREPROC_MOBILENET)
+        _check(eng, w, x, _lib.PREPROC_MOBILENET, precision=precision)
+    x = synth.synth_images(2, 2176, 3840, seed=5)
+    _check(eng, w, x, _lib.PREPROC_MOBILENET, precision=precision)
 
 
-def test_chunking_is_invisible():
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_chunking_is_invisible(precision):
     w = onet.init_weights(2, seed=3)
-    eng = _engine(n_classes=2)
+    eng = _engine(n_classes=2, precision=precision)
     eng.set_weights(w)
-    x = synth.synth_images(7, 64, 64, seed=8)
+    x = synth.synth_images(37, 64, 64, seed=8)
     a = eng.forward(x, _lib.PREPROC_MOBILENET)
     eng.set_option("chunk", 3)
     b = eng.forward(x, _lib.PREPROC_MOBILENET)
