@@ -34,7 +34,7 @@ def _check(eng, w, x, pre, fml=True, precision="fp32"):
     return got, ref
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_config_a_parity(precision):
     """BASELINE configs[0]: 8 x 512x512 grayscale, random-init weights."""
     w = onet.init_weights(0, seed=1234)
@@ -51,7 +51,7 @@ def test_config_a_parity(precision):
     _check(eng, w, xf, _lib.PREPROC_NONE, precision=precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("fml", [True, False])
 @pytest.mark.parametrize("n_classes,grey", [(0, True), (6, True), (26, True), (3, False)])
 def test_variants(fml, n_classes, grey, precision):
@@ -61,7 +61,7 @@ def test_variants(fml, n_classes, grey, precision):
     x = synth.synth_images(3, 64, 192, seed=2, channels=1 if grey else 3)
     got, ref = _check(eng, w, x, _lib.PREPROC_MOBILENET, fml=fml, precision=precision)
     assert got.shape == (3, 16, 48, 1 + n_classes)
-    assert np.abs(got - ref).max() <= (1e-4 if precision == "fp32" else 2e-2)
+    assert np.abs(got - ref).max() <= {"fp32": 1e-4, "tf32": 2e-2, "bf16": 1e-1}[precision]
     # float input = already preprocessed (Keras semantics), and raw uint8 without preprocessing
     xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
     got_f = eng.forward(xf, _lib.PREPROC_NONE)
@@ -69,7 +69,7 @@ def test_variants(fml, n_classes, grey, precision):
     _check(eng, w, x, _lib.PREPROC_NONE, fml=fml, precision=precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_ragged_and_large_shapes(precision):
     """Non-square, sides that are multiples of 16 but not of 64, and the 2176x3840 scan (config C)."""
     w = onet.init_weights(0, seed=9)
@@ -82,7 +82,7 @@ def test_ragged_and_large_shapes(precision):
     _check(eng, w, x, _lib.PREPROC_MOBILENET, precision=precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_chunking_is_invisible(precision):
     w = onet.init_weights(2, seed=3)
     eng = _engine(n_classes=2, precision=precision)

@@ -53,3 +53,23 @@ def test_tf32_delta_taps(eng):
         got = eng.debug_dilated_layer(x, layer, "tf32")
         ref = _ref_layer(w, x, layer, tf32=True)
         assert np.abs(got - ref).max() <= 1e-5, (layer, d)
+
+
+def _round_bf16(a):
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u + np.uint32(0x7FFF) + ((u >> 16) & 1)) & np.uint32(0xFFFF0000))       # round to nearest even
+    return r.view(np.float32)
+
+
+@pytest.mark.parametrize("layer", range(6))
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 32, 256), (3, 20, 36), (1, 136, 240)])
+def test_bf16_layer_matches_oracle(eng, layer, shape):
+    """kind::f16 (bf16 operands, fp32 accumulate): against the oracle evaluated on bf16-rounded inputs and
+    weights only the fp32 accumulation order remains."""
+    rng = np.random.default_rng(layer * 10 + shape[1])
+    x = _round_bf16(np.maximum(rng.normal(0, 1, size=shape + (24,)), 0).astype(np.float32))
+    w = onet.init_weights(0, seed=1234)
+    got = eng.debug_dilated_layer(x, layer, "bf16")
+    k, b = _round_bf16(w[9 + 2 * layer]), w[10 + 2 * layer]
+    ref = np.maximum(onet._conv3x3_np(x.astype(np.float64), k.astype(np.float64), onet.DILATIONS[layer]) + b, 0)
+    assert np.abs(got - ref).max() <= 2e-4, np.abs(got - ref).max()

@@ -349,10 +349,12 @@ static int ensure_maps(ubd_handle h, int n, int mh, int mw) {
   const bool grow = bytes > h->mapA.cap || bytes > h->mapB.cap;
   ENSURE(h->mapA, bytes);
   ENSURE(h->mapB, bytes);
-  if (grow || h->map_h != mh || h->map_w != mw || h->map_n < n) {
+  if (h->precision == UBD_BF16) ENSURE(h->mapC, bytes);
+  // the interior of one layout (fp32: 6 planes, bf16: 3 planes per row) overlaps the pads of the other
+  if (grow || h->map_h != mh || h->map_w != mw || h->map_n < n || h->map_prec != h->precision) {
     UBD_CUDA(cudaMemsetAsync(h->mapA.p, 0, h->mapA.cap, h->stream));
     UBD_CUDA(cudaMemsetAsync(h->mapB.p, 0, h->mapB.cap, h->stream));
-    h->map_h = mh; h->map_w = mw; h->map_n = n;
+    h->map_h = mh; h->map_w = mw; h->map_n = n; h->map_prec = h->precision;
   }
   return UBD_OK;
 }
@@ -367,11 +369,12 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
   const int chunk = pick_chunk(h, n, H, W);
   const int schunk = pick_stem_chunk(h, chunk, H, W);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
-  if (h->precision != UBD_TF32) ENSURE(h->act1, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
+  if (h->precision == UBD_FP32) ENSURE(h->act1, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
   ENSURE(h->act2, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
   { int rc_ = ensure_maps(h, chunk, h4, w4); if (rc_) return rc_; }
   const size_t img_stride = (size_t)H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
-  const size_t map_img = act_elems(1, h4, w4, UBD_MAP_PAD);
+  // 16-byte units per image of the L3 output map: 6 planes (fp32 / tf32) or 3 planes (bf16)
+  const size_t map_img = act_elems(1, h4, w4, UBD_MAP_PAD) / (h->precision == UBD_BF16 ? 2 : 1);
   size_t copy_k = 0;
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int cn = std::min(chunk, n - c0);
@@ -396,7 +399,7 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
       }
       ProfScope ps(h, &h->prof_stem);
       float4* a3 = A + (size_t)s0 * map_img;
-      if (h->precision == UBD_TF32) rc = run_stem_tc(h, img, in_dtype, preproc, sn, H, W, (float4*)h->act2.p, a3);
+      if (h->precision != UBD_FP32) rc = run_stem_tc(h, img, in_dtype, preproc, sn, H, W, (float4*)h->act2.p, a3);
       else rc = run_stem(h, img, in_dtype, preproc, sn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, a3);
       if (rc) return rc;
     }
@@ -405,10 +408,13 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
       ProfScope ps(h, &h->prof_dil);
       const float* w = h->d_params + h->spec.off[9 + 2 * l];
       const float* b = h->d_params + h->spec.off[10 + 2 * l];
+      const bool last = l == UBD_NLAYERS_DIL - 1;
+      float4* dst = (last && h->precision == UBD_BF16) ? (float4*)h->mapC.p : B;      // fp32 map for the head
       if (h->precision == UBD_FP32) rc = launch_dil_fp32(h, A, B, w, b, nullptr, cn, h4, w4, kDilations[l], 0);
-      else rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*round_out=*/l < UBD_NLAYERS_DIL - 1);
+      else rc = tc_launch_dilconv(h, A, dst, l, cn, h4, w4, kDilations[l], /*out_mode=*/last ? 1 : 0);
       if (rc) return rc;
       std::swap(A, B);
+      if (last && h->precision == UBD_BF16) A = dst;
     }
     { ProfScope ps(h, &h->prof_head);
       rc = launch_head(h, A, d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
@@ -655,6 +661,20 @@ __global__ void planar_to_nhwc_kernel(const float4* __restrict__ src, float* __r
   }
 }
 
+__global__ void nhwc_to_planar_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int n, int hh, int ww) {
+  const size_t npx = (size_t)hh * ww;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * npx) return;
+  const size_t img = i / npx, p = i % npx;
+  const int y = (int)(p / ww), x = (int)(p % ww);
+  const size_t wp = ww + 2 * UBD_MAP_PAD;
+  for (int g = 0; g < 3; ++g) {
+    const float* s = src + i * UBD_NF + 8 * g;
+    dst[((img * hh + y) * 3 + g) * wp + UBD_MAP_PAD + x] =
+        make_uint4(tc::pack_bf16x2(s[0], s[1]), tc::pack_bf16x2(s[2], s[3]), tc::pack_bf16x2(s[4], s[5]), tc::pack_bf16x2(s[6], s[7]));
+  }
+}
+
 extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float* out_nhwc, int layer,
                                        int n, int mh, int mw, int precision) {
   if (!h) return UBD_ERR_ARG;
@@ -667,7 +687,20 @@ extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float
   { int rc_ = ensure_maps(h, n, mh, mw); if (rc_) return rc_; }
   UBD_CUDA(cudaMemcpyAsync(h->t_scratch.p, in_nhwc, elems * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   const unsigned blocks = (unsigned)(((size_t)n * mh * mw + 255) / 256);
-  nhwc_to_planar_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->t_scratch.p, (float4*)h->mapA.p, n, mh, mw); LAUNCH_CHECK();
+  if (precision == UBD_BF16) {
+    // bf16 input layout shares the buffer with fp32 layouts of earlier calls: clear the pads
+    UBD_CUDA(cudaMemsetAsync(h->mapA.p, 0, h->mapA.cap, h->stream));
+    UBD_CUDA(cudaMemsetAsync(h->mapB.p, 0, h->mapB.cap, h->stream));
+    h->map_prec = -1;
+    nhwc_to_planar_bf16_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->t_scratch.p, (uint4*)h->mapA.p, n, mh, mw); LAUNCH_CHECK();
+  } else {
+    if (h->map_prec == UBD_BF16 || h->map_prec == -1) {
+      UBD_CUDA(cudaMemsetAsync(h->mapA.p, 0, h->mapA.cap, h->stream));
+      UBD_CUDA(cudaMemsetAsync(h->mapB.p, 0, h->mapB.cap, h->stream));
+      h->map_prec = UBD_FP32;
+    }
+    nhwc_to_planar_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->t_scratch.p, (float4*)h->mapA.p, n, mh, mw); LAUNCH_CHECK();
+  }
   const float* w = h->d_params + h->spec.off[9 + 2 * layer];
   const float* b = h->d_params + h->spec.off[10 + 2 * layer];
   int rc;
@@ -676,7 +709,7 @@ extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float
   } else {
     const int saved = h->precision;
     h->precision = precision;
-    rc = tc_launch_dilconv(h, (float4*)h->mapA.p, (float4*)h->mapB.p, layer, n, mh, mw, kDilations[layer], 0);
+    rc = tc_launch_dilconv(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1);
     h->precision = saved;
   }
   if (rc) return rc;

@@ -37,8 +37,8 @@ struct ubd_handle_s {
 
   // inference workspaces
   DevBuf d_images, d_logits, d_mask;
-  DevBuf act1, act2, mapA, mapB;
-  int map_h = 0, map_w = 0, map_n = 0;     // shape the padded maps were last zeroed for
+  DevBuf act1, act2, mapA, mapB, mapC;     // mapC: fp32 output of the last layer in bf16 mode
+  int map_h = 0, map_w = 0, map_n = 0, map_prec = -1;     // shape the padded maps were last zeroed for
   DevBuf outer;
   DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
   DevBuf stem_wimg;               // pointwise B images of L2 / L3 for the tensor-core stem
@@ -53,7 +53,7 @@ struct ubd_handle_s {
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 
   std::vector<DevBuf*> all_bufs() {
-    return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &outer, &parent, &labels, &slot_of, &comps,
+    return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
             &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc_trace, &stem_wimg, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
   }

@@ -68,7 +68,8 @@ __device__ __forceinline__ void pw_issue(PwSmem<ROWS>& S, uint32_t tmem_base) {
 }
 
 // Epilogue of one tile: warp w reads TMEM quadrant w&3 of segments (w>>2), (w>>2)+2, ...
-template <bool ROUND, int ROWS>
+// MODE 0: fp32 as is; 1: fp32 rounded to the tf32 grid; 2: bf16, 3 planes of 8 channels.
+template <int MODE, int ROWS>
 __device__ __forceinline__ void pw_epilogue(PwSmem<ROWS>& S, uint32_t tmem_base, float4* __restrict__ out, int n, int y0, int x0,
                                             int Ho, int Wo, int opad) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quad = warp & 3;
@@ -87,15 +88,23 @@ __device__ __forceinline__ void pw_epilogue(PwSmem<ROWS>& S, uint32_t tmem_base,
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     const int y = y0 + r, x = x0 + quad * 32 + lane;
     if (y < Ho && x < Wo) {
+      float o[UBD_NF];
 #pragma unroll
-      for (int g = 0; g < UBD_NG; ++g) {
-        float4 o;
-        o.x = fmaxf(__uint_as_float(v[4 * g + 0]) + S.bias[4 * g + 0], 0.f);
-        o.y = fmaxf(__uint_as_float(v[4 * g + 1]) + S.bias[4 * g + 1], 0.f);
-        o.z = fmaxf(__uint_as_float(v[4 * g + 2]) + S.bias[4 * g + 2], 0.f);
-        o.w = fmaxf(__uint_as_float(v[4 * g + 3]) + S.bias[4 * g + 3], 0.f);
-        if (ROUND) { o.x = tc::round_tf32(o.x); o.y = tc::round_tf32(o.y); o.z = tc::round_tf32(o.z); o.w = tc::round_tf32(o.w); }
-        out[act_index(n, g, y, x, Ho, Wo, opad)] = o;
+      for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + S.bias[c], 0.f);
+      if constexpr (MODE == 2) {
+        uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)n * Ho + y) * tc::NG_BF16) * (size_t)(Wo + 2 * opad) + opad + x;
+#pragma unroll
+        for (int g = 0; g < tc::NG_BF16; ++g)
+          dst[(size_t)g * (Wo + 2 * opad)] =
+              make_uint4(tc::pack_bf16x2(o[8 * g], o[8 * g + 1]), tc::pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                         tc::pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), tc::pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+      } else {
+#pragma unroll
+        for (int g = 0; g < UBD_NG; ++g) {
+          float4 q = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+          if (MODE == 1) { q.x = tc::round_tf32(q.x); q.y = tc::round_tf32(q.y); q.z = tc::round_tf32(q.z); q.w = tc::round_tf32(q.w); }
+          out[act_index(n, g, y, x, Ho, Wo, opad)] = q;
+        }
       }
     }
   }
@@ -301,7 +310,7 @@ stem12_tc_kernel(const TIn* __restrict__ img, float4* __restrict__ act2, const f
       // (c) previous pair: its MMAs are done by now -> epilogue; also frees the A tiles
       if (p > 0) {
         wait_mma(S.pw, (mma_count - 1) & 1, gerr);
-        pw_epilogue<false>(S.pw, tmem_base, act2, n, y - 2, x0, H2, W2, 0);
+        pw_epilogue<0>(S.pw, tmem_base, act2, n, y - 2, x0, H2, W2, 0);
         tc::tc_fence_before();
       }
       // (d) L2 depthwise of rows y, y+1 -> A segments 0, 1.  Task = (plane, pixel column).
@@ -368,7 +377,7 @@ stem12_tc_kernel(const TIn* __restrict__ img, float4* __restrict__ act2, const f
     }
     // ---- last pair of the item
     wait_mma(S.pw, (mma_count - 1) & 1, gerr);
-    pw_epilogue<false>(S.pw, tmem_base, act2, n, y0 + 2 * (npairs - 1), x0, H2, W2, 0);
+    pw_epilogue<0>(S.pw, tmem_base, act2, n, y0 + 2 * (npairs - 1), x0, H2, W2, 0);
     tc::tc_fence_before();
     __syncthreads();
   }
@@ -386,6 +395,7 @@ struct Smem3 {
   float dw3[9 * UBD_NF];
 };
 
+template <int OUT_MODE>
 __global__ void __launch_bounds__(THREADS, 3)
 stem3_tc_kernel(const float4* __restrict__ act2, float4* __restrict__ act3, const float* __restrict__ params,
                 int64_t off_dw3, const uint8_t* __restrict__ wb3, int N, int H2, int W2, int pad_t, int pad_l, int* gerr) {
@@ -428,7 +438,7 @@ stem3_tc_kernel(const float4* __restrict__ act2, float4* __restrict__ act3, cons
     __syncthreads();
     if (warp == 0) pw_issue(S.pw, tmem_base);
     wait_mma(S.pw, it & 1, gerr);
-    pw_epilogue<true>(S.pw, tmem_base, act3, n, y0, x0, H4, W4, UBD_MAP_PAD);
+    pw_epilogue<OUT_MODE>(S.pw, tmem_base, act3, n, y0, x0, H4, W4, UBD_MAP_PAD);
     tc::tc_fence_before();
     __syncthreads();
   }
@@ -492,19 +502,23 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
   }
   if (rc) return rc;
   {
-    static bool attr_set = false;
     const size_t smem = sizeof(stem::Smem3) + 128;
+    static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(stem::stem3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(stem::stem3_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(stem::stem3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(stem::stem3_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(stem::stem3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(stem::stem3_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       attr_set = true;
     }
     const int H2 = H / 2, W2 = W / 2;
     const int ntiles = n * ((H2 / 2 + stem::R3 - 1) / stem::R3) * ((W2 / 2 + stem::SEGPX - 1) / stem::SEGPX);
     const int grid = std::min(ntiles, 3 * h->n_sm);
-    stem::stem3_tc_kernel<<<grid, stem::THREADS, smem, h->stream>>>(act2, act3, h->d_params, h->spec.off[6],
-                                                                    (const uint8_t*)h->stem_wimg.p + stem::PW_WB_BYTES,
-                                                                    n, H2, W2, p2, p2, tc_err_flag(h));
+    const uint8_t* wb3 = (const uint8_t*)h->stem_wimg.p + stem::PW_WB_BYTES;
+    if (h->precision == UBD_BF16)
+      stem::stem3_tc_kernel<2><<<grid, stem::THREADS, smem, h->stream>>>(act2, act3, h->d_params, h->spec.off[6], wb3, n, H2, W2, p2, p2, tc_err_flag(h));
+    else
+      stem::stem3_tc_kernel<1><<<grid, stem::THREADS, smem, h->stream>>>(act2, act3, h->d_params, h->spec.off[6], wb3, n, H2, W2, p2, p2, tc_err_flag(h));
     ++h->launches;
     UBD_CUDA(cudaGetLastError());
   }

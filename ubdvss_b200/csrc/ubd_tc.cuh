@@ -31,6 +31,7 @@
 //              it has seen tmem_full of a row's last segment every MMA that read the top row of that
 //              window has completed, whichever warp issued it.
 #pragma once
+#include <cuda_bf16.h>
 #include "ubd_handle.cuh"
 
 namespace tc {
@@ -48,6 +49,14 @@ constexpr int N_MMA = 27;                     // 9 taps x 3 K-pairs (8 tf32 each
 constexpr int B_TILE_BYTES = UMMA_N * 8 * 4;  // 1024: [2 K cores][4 oc groups][8 rows][16 B]
 constexpr int W_BYTES = N_MMA * B_TILE_BYTES; // 27648
 constexpr int WB_BYTES = W_BYTES + 128;       // + bias[24] padded to 32 floats
+// bf16 variant: maps are 3 planes of 8 channels per 16 B; kind::f16 consumes K = 16 (two planes) per
+// MMA.  27 (tap, plane) K-cores pair up as: planes 0+1 of every tap (9 MMAs, LBO = plane stride),
+// plane 2 of taps dx=-1 and dx=0 of one row (3 MMAs, LBO = d pixels), plane 2 of tap dx=+1 with a
+// zero B core (3 MMAs): 15 MMAs per segment, each the same 5 KB operand read as a tf32 MMA.
+constexpr int N_MMA_BF16 = 15;
+constexpr int NG_BF16 = 3;
+constexpr int W_BYTES_BF16 = N_MMA_BF16 * B_TILE_BYTES;   // 15360 (32 oc x 16 ic x 2 B per MMA)
+constexpr int WB_BYTES_BF16 = W_BYTES_BF16 + 128;
 constexpr int RQ = 8;                         // output rows per work item
 constexpr int THREADS = 224;                  // producer, MMA issuer A, 4 epilogue warps, MMA issuer B
 constexpr int ZERO_BYTES = MAX_SLOT_BYTES;
@@ -118,6 +127,16 @@ constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, 
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 32 (cute::UMMA::InstrDescriptor).
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((UMMA_N >> 3) << 17) | ((SEG >> 4) << 24);
 
+// kind::f16 with bf16 operands, fp32 accumulate, K-major A and B, M = 128, N = 32.
+constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((UMMA_N >> 3) << 17) | ((SEG >> 4) << 24);
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_BF16), "r"(accumulate), "r"(0u) : "memory");
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -156,12 +175,23 @@ __device__ __forceinline__ float round_tf32(float v) {
   return __uint_as_float(u);
 }
 
-// in/out: padded row-interleaved maps (pad = PAD) of n_imgs images; wb: this layer's B image
-// (W_BYTES) followed by bias[32]; sw: strip width (128 or 256).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// in/out: padded row-interleaved maps (pad = PAD) of n_imgs images, in 16-byte units: tf32 maps have
+// 6 planes of float4, bf16 maps 3 planes of 8 x bf16.  wb: this layer's B image followed by bias[32];
+// sw: strip width (128 or 256).  out_mode: 0 = same format as the input, tf32 output rounded (rna);
+// 1 = fp32 6-plane output without rounding (last layer, feeds the fp32 head).
+template <bool BF16>
 __global__ void __launch_bounds__(THREADS, 1)
-dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, const uint8_t* __restrict__ wb,
-                    const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int round_out, int* gerr,
-                    long long* trace) {
+dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
+                  const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int out_mode, int* gerr,
+                  long long* trace) {
+  constexpr int NGI = BF16 ? NG_BF16 : UBD_NG;                  // planes of the input map
+  constexpr uint32_t WBB = BF16 ? WB_BYTES_BF16 : WB_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform
@@ -191,14 +221,14 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
   const uint32_t slots0 = smem_u32(S.slots);
   const int wp = w + 2 * PAD;                              // global row pitch in pixels
   const uint32_t plane_bytes = (uint32_t)(sw + 2 * PAD) * 16;   // slot plane stride = LBO
-  const uint32_t slot_bytes = UBD_NG * plane_bytes;
+  const uint32_t slot_bytes = NGI * plane_bytes;
   const bool one_copy = (w == sw);                         // slot is an exact image of the global row block
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (elect_one()) {
-      mbar_expect_tx(smem_u32(&S.wbar), WB_BYTES);
-      bulk_g2s(smem_u32(S.wimg), wb, WB_BYTES, smem_u32(&S.wbar));
+      mbar_expect_tx(smem_u32(&S.wbar), WBB);
+      bulk_g2s(smem_u32(S.wimg), wb, WBB, smem_u32(&S.wbar));
     }
     uint32_t lseq = 0;
     bool ok = true;
@@ -206,7 +236,7 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
       Item it;
       if (!sched.get(idx, it)) continue;
       const uint32_t copy_bytes = (uint32_t)it.copy_px * 16;
-      const uint32_t row_bytes = one_copy ? slot_bytes : UBD_NG * copy_bytes;
+      const uint32_t row_bytes = one_copy ? slot_bytes : NGI * copy_bytes;
       for (int q = it.q0 - 1; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
         const uint32_t slot = lseq % NS;
         TC_TRACE(0, 0, clock64());
@@ -217,15 +247,15 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
         const uint32_t dst = slots0 + slot * slot_bytes;
         const bool valid = q >= 0 && q < it.nq;
         // source of plane 0: padded pixel x0 of row y (the strip's left halo starts there)
-        const float4* src = valid ? in + (((size_t)it.n * h + (it.r + q * d)) * UBD_NG) * wp + it.x0
-                                  : reinterpret_cast<const float4*>(zeros);
+        const uint4* src = valid ? in + (((size_t)it.n * h + (it.r + q * d)) * NGI) * wp + it.x0
+                                 : reinterpret_cast<const uint4*>(zeros);
         if (elect_one()) {
           mbar_expect_tx(bar, row_bytes);
           if (one_copy) {
             bulk_g2s(dst, src, slot_bytes, bar);
           } else {
 #pragma unroll
-            for (int g = 0; g < UBD_NG; ++g)
+            for (int g = 0; g < NGI; ++g)
               bulk_g2s(dst + g * plane_bytes, valid ? src + (size_t)g * wp : src, copy_bytes, bar);
           }
         }
@@ -267,14 +297,36 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
           for (int t = 0; t < 3; ++t)
             a_row[t] = ((((slots0 + ((lbase + j + t) % NS) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo) + PAD;
           if (elect_one()) {
+            if constexpr (!BF16) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap % 3 - 1;
-              const uint32_t a_lo = a_row[dy] + (uint32_t)(s * SEG + dx * d);
+              for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3, dx = tap % 3 - 1;
+                const uint32_t a_lo = a_row[dy] + (uint32_t)(s * SEG + dx * d);
 #pragma unroll
-              for (int kp = 0; kp < 3; ++kp) {
-                umma_tf32(tmem_d, make_desc(a_lo + kp * kp_units, DESC_HI),
-                          make_desc(b_lo0 + (tap * 3 + kp) * (B_TILE_BYTES >> 4), DESC_HI), (tap | kp) != 0);
+                for (int kp = 0; kp < 3; ++kp) {
+                  umma_tf32(tmem_d, make_desc(a_lo + kp * kp_units, DESC_HI),
+                            make_desc(b_lo0 + (tap * 3 + kp) * (B_TILE_BYTES >> 4), DESC_HI), (tap | kp) != 0);
+                }
+              }
+            } else {
+              const uint32_t plane_units = plane_bytes >> 4;
+              const uint32_t lbo_mask = ~(0x3FFFu << 16);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {                 // planes 0 + 1 of every tap
+                const int dy = tap / 3, dx = tap % 3 - 1;
+                umma_bf16(tmem_d, make_desc(a_row[dy] + (uint32_t)(s * SEG + dx * d), DESC_HI),
+                          make_desc(b_lo0 + tap * (B_TILE_BYTES >> 4), DESC_HI), tap != 0);
+              }
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                // plane 2 of taps dx = -1 (K core 0) and dx = 0 (K core 1): LBO = d pixels
+                const uint32_t a2 = (a_row[dy] & lbo_mask) + 2 * plane_units + (uint32_t)(s * SEG);
+                umma_bf16(tmem_d, make_desc((a2 - d) | ((uint32_t)d << 16), DESC_HI),
+                          make_desc(b_lo0 + (9 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u);
+                // plane 2 of tap dx = +1; the B image's second K core is zero and LBO = 0 makes the A
+                // side re-read the same (finite) core instead of whatever lies beyond the slot
+                umma_bf16(tmem_d, make_desc(a2 + d, DESC_HI),
+                          make_desc(b_lo0 + (12 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u);
               }
             }
             umma_commit(smem_u32(&S.tfull[acc]));
@@ -291,7 +343,8 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
     bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 5);
     float bias[UBD_NF];
 #pragma unroll
-    for (int c = 0; c < UBD_NF; ++c) bias[c] = ok ? S.bias[c] : 0.f;
+    for (int c = 0; c < UBD_NF; ++c)
+      bias[c] = ok ? reinterpret_cast<const float*>(S.wimg + (BF16 ? W_BYTES_BF16 : W_BYTES))[c] : 0.f;
     uint32_t it_rows_plus2 = 0;
     uint32_t oseq = 0, lbase = 0;
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x, lbase += it_rows_plus2) {
@@ -332,16 +385,24 @@ dilconv_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, con
           if (lane == 0) mbar_arrive(smem_u32(&S.tempty[acc]));
           const int x = it.x0 + s * SEG + quad * 32 + lane;
           if (x < w) {
-            float4* o_px = out + act_index(it.n, 0, y, x, h, w, PAD);
+            float o[UBD_NF];
 #pragma unroll
-            for (int g = 0; g < UBD_NG; ++g) {
-              float4 o;
-              o.x = fmaxf(__uint_as_float(v[4 * g + 0]) + bias[4 * g + 0], 0.f);
-              o.y = fmaxf(__uint_as_float(v[4 * g + 1]) + bias[4 * g + 1], 0.f);
-              o.z = fmaxf(__uint_as_float(v[4 * g + 2]) + bias[4 * g + 2], 0.f);
-              o.w = fmaxf(__uint_as_float(v[4 * g + 3]) + bias[4 * g + 3], 0.f);
-              if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-              o_px[(size_t)g * wp] = o;
+            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
+            if (BF16 && out_mode == 0) {
+              uint4* o_px = out + (((size_t)it.n * h + y) * NG_BF16) * wp + PAD + x;
+#pragma unroll
+              for (int g = 0; g < NG_BF16; ++g)
+                o_px[(size_t)g * wp] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                                                  pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+            } else {
+              uint4* o_px = out + (((size_t)it.n * h + y) * UBD_NG) * wp + PAD + x;
+              const bool rnd = !BF16 && out_mode == 0;
+#pragma unroll
+              for (int g = 0; g < UBD_NG; ++g) {
+                float4 q = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                if (rnd) { q.x = round_tf32(q.x); q.y = round_tf32(q.y); q.z = round_tf32(q.z); q.w = round_tf32(q.w); }
+                o_px[(size_t)g * wp] = *reinterpret_cast<uint4*>(&q);
+              }
             }
           }
           if (warp == 2) { TC_TRACE(2, 2, clock64()); ++tr_n; }
@@ -376,16 +437,44 @@ __global__ void build_wimg_kernel(const float* __restrict__ params, const int64_
   for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[W_BYTES / 4 + i] = i < UBD_NF ? B[i] : 0.f;
 }
 
+// bf16 B images: per MMA [2 K cores][4 oc groups][8 oc rows][8 ic x bf16]; MMA list as in the kernel:
+// 0..8 = tap t, ic 0..15; 9..11 = row dy: core0 = tap (dy,-1) ic 16..23, core1 = tap (dy,0) ic 16..23;
+// 12..14 = row dy: core0 = tap (dy,+1) ic 16..23, core1 = 0.  Then the fp32 bias.
+__global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
+                                       const int64_t* __restrict__ boff, uint8_t* __restrict__ wimg_all) {
+  const int layer = blockIdx.x;
+  const float* K = params + koff[layer];
+  const float* B = params + boff[layer];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wimg_all + (size_t)layer * WB_BYTES_BF16);
+  for (int i = threadIdx.x; i < W_BYTES_BF16 / 2; i += blockDim.x) {
+    const int m = i / 512, rem = i % 512;                       // 512 bf16 per MMA image
+    const int kcore = rem / 256, ngroup = (rem % 256) / 64, row = (rem % 64) / 8, col = rem % 8;
+    const int oc = ngroup * 8 + row;
+    int tap = -1, ic = 0;
+    if (m < 9) { tap = m; ic = kcore * 8 + col; }
+    else if (m < 12) { tap = (m - 9) * 3 + kcore; ic = 16 + col; }            // dx = -1 (core 0), dx = 0 (core 1)
+    else if (kcore == 0) { tap = (m - 12) * 3 + 2; ic = 16 + col; }           // dx = +1
+    const float v = (tap >= 0 && oc < UBD_NF) ? K[(tap * UBD_NF + ic) * UBD_NF + oc] : 0.f;
+    dst[i] = __float2bfloat16_rn(v);
+  }
+  float* bias = reinterpret_cast<float*>(wimg_all + (size_t)layer * WB_BYTES_BF16 + W_BYTES_BF16);
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) bias[i] = i < UBD_NF ? B[i] : 0.f;
+}
+
 }  // namespace tc
 
 static void tc_setup_attributes() {
-  cudaFuncSetAttribute(tc::dilconv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
 }
 
-// tc_weights buffer: [6 layers x WB_BYTES][zero page][int err flag][offsets]
+// tc_weights buffer: [6 x WB_BYTES tf32 images][6 x WB_BYTES_BF16 bf16 images][zero page][err flag][offsets]
+static constexpr size_t kTcImgTf32 = (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
+static constexpr size_t kTcImgBf16 = (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16;
+static constexpr size_t kTcZeroOff = (kTcImgTf32 + kTcImgBf16 + 127) & ~(size_t)127;
+
 static int tc_prepare(ubd_handle h) {
-  const size_t img = (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
-  const size_t total = img + tc::ZERO_BYTES + 256;
+  const size_t total = kTcZeroOff + tc::ZERO_BYTES + 256;
   if (!h->tc_weights.p) {
     UBD_CUDA(cudaMalloc(&h->tc_weights.p, total));
     h->tc_weights.cap = total;
@@ -395,11 +484,12 @@ static int tc_prepare(ubd_handle h) {
   if (h->tc_weights_dirty) {
     int64_t offs[12];
     for (int l = 0; l < 6; ++l) { offs[l] = h->spec.off[9 + 2 * l]; offs[6 + l] = h->spec.off[10 + 2 * l]; }
-    int64_t* d_offs = reinterpret_cast<int64_t*>((uint8_t*)h->tc_weights.p + img + tc::ZERO_BYTES + 64);
+    int64_t* d_offs = reinterpret_cast<int64_t*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES + 64);
     UBD_CUDA(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, h->stream));
     UBD_CUDA(cudaStreamSynchronize(h->stream));      // offs is a stack array
     tc::build_wimg_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p);
-    ++h->launches;
+    tc::build_wimg_bf16_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p + kTcImgTf32);
+    h->launches += 2;
     UBD_CUDA(cudaGetLastError());
     h->tc_weights_dirty = false;
   }
@@ -407,24 +497,31 @@ static int tc_prepare(ubd_handle h) {
 }
 
 static inline int* tc_err_flag(ubd_handle h) {
-  return reinterpret_cast<int*>((uint8_t*)h->tc_weights.p + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES + tc::ZERO_BYTES);
+  return reinterpret_cast<int*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES);
 }
 
-static int tc_launch_dilconv(ubd_handle h, const float4* in, float4* out, int layer, int n, int hh, int ww, int d,
-                             int round_out) {
-  if (h->precision != UBD_TF32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path: only tf32 is built in this revision");
+// in / out: padded maps in the precision's layout (tf32: 6 float4 planes, bf16: 3 planes of 8 bf16).
+// out_mode 1 writes fp32 6-plane output (last layer -> fp32 head).
+static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
+                             int out_mode) {
+  if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
   int rc = tc_prepare(h);
   if (rc) return rc;
+  const bool bf16 = h->precision == UBD_BF16;
   const uint8_t* base = (const uint8_t*)h->tc_weights.p;
-  const uint8_t* wb = base + (size_t)layer * tc::WB_BYTES;
-  const uint8_t* zeros = base + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
+  const uint8_t* wb = bf16 ? base + kTcImgTf32 + (size_t)layer * tc::WB_BYTES_BF16 : base + (size_t)layer * tc::WB_BYTES;
+  const uint8_t* zeros = base + kTcZeroOff;
   const int sw = ww <= tc::SEG ? tc::SEG : tc::MAX_SW;
   const int n_strips = (ww + sw - 1) / sw;
   const int n_chunks = ((hh + d - 1) / d + tc::RQ - 1) / tc::RQ;
   const long long items = (long long)n * n_strips * d * n_chunks;
   const int grid = (int)std::min<long long>(items, h->n_sm);
-  tc::dilconv_tf32_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>(in, out, wb, zeros, n, hh, ww, d, sw, round_out, tc_err_flag(h),
-                                                                            (long long*)h->tc_trace.p);
+  if (bf16)
+    tc::dilconv_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw,
+                                                                                 out_mode, tc_err_flag(h), (long long*)h->tc_trace.p);
+  else
+    tc::dilconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw,
+                                                                                  out_mode, tc_err_flag(h), (long long*)h->tc_trace.p);
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
