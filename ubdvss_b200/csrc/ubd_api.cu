@@ -459,8 +459,13 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
   HostTimer* ht_enq = new HostTimer(h, 1);
   ProfScope* ps_ccl = new ProfScope(h, &h->prof_ccl);
   UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
-  ccl_init_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_merge1_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  dim3 lgrid32((mw + CCL_T - 1) / CCL_T, (mh + CCL_T - 1) / CCL_T, n);
+  ccl_local_kernel<<<lgrid32, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  const int n_border = ((mh - 1) / CCL_T) * mw + ((mw - 1) / CCL_T) * 2 * mh;
+  if (n_border > 0) {
+    dim3 bgrid2((unsigned)((n_border + 255) / 256), n);
+    ccl_border_kernel<<<bgrid2, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  }
   uint8_t* outer = (uint8_t*)h->outer.p;
   ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, outer, mh, mw, pstride); LAUNCH_CHECK();
   dim3 bgrid((unsigned)((2 * (mh + mw) + 255) / 256), n);

@@ -1,7 +1,9 @@
 // GPU connected components with cv2.findContours(RETR_EXTERNAL) semantics (utils.py:51-60,
 // segmap_manager.py:54-69; exact statement in SURVEY.md 8a/P2 and oracle/postproc.py::ccl_spec):
-//   1. union-find over all pixels: foreground 8-connected, background 4-connected; the background
-//      sets that own a border pixel are flagged "outer" (connected to the outside of the image);
+//   1. union-find over all pixels: foreground 8-connected, background 4-connected -- tile-local in
+//      shared memory (warp-ballot run starts + atomicMin links inside 32x32 tiles), then a boundary
+//      merge over the tile borders; the background sets that own an image-border pixel are flagged
+//      "outer" (connected to the outside of the image);
 //   2. "filled" = foreground or background whose set is not outer (holes); union 8-adjacent filled;
 //   3. label = root = smallest raster index of the filled component (first pixel in raster order);
 //   4. per-component reductions: bbox, foreground / filled pixel counts, 2x2 bit-quad counts
@@ -36,55 +38,141 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-// parent[i] = start of the horizontal same-class run of i inside its 32-pixel warp segment
-// (ballot), so horizontal links inside a segment cost no atomics.
-__global__ void __launch_bounds__(256)
-ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
-  const int n = blockIdx.z;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (y >= h) return;
-  const uint8_t* m = mask + (size_t)n * h * w;
-  int* par = parent + (size_t)n * pstride;
-  const bool in = x < w;
-  const bool fg = in && m[(size_t)y * w + x] != 0;
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned bits = __ballot_sync(0xffffffffu, fg);
-  if (in) {
-    const unsigned same = fg ? bits : ~bits;                 // lanes of my class
-    const unsigned below = (~same) & ((1u << lane) - 1u);    // other-class lanes left of me
-    const int start = below ? 32 - __clz(below) : 0;         // first lane of my run
-    par[(size_t)y * w + x] = y * w + (x - (int)lane + start);
+// ------------------------------------------------------------------------------------------------
+// Phase 1 (foreground 8-connectivity, background 4-connectivity), tile-local then boundary merge.
+// ------------------------------------------------------------------------------------------------
+constexpr int CCL_T = 32;     // tile side; block = 32 x 8 threads, 4 rows per thread
+
+__device__ __forceinline__ int suf_find(const int* par, int i) {      // shared-memory find
+  int p;
+  while ((p = *((volatile const int*)(par + i))) != i) i = p;
+  return i;
+}
+__device__ __forceinline__ void suf_union(int* par, int a, int b) {   // shared-memory union (atomicMin)
+  while (true) {
+    a = suf_find(par, a);
+    b = suf_find(par, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    const int old = atomicMin(par + a, b);
+    if (old == a) return;
+    a = old;
   }
 }
 
-// Phase 1: foreground 8-connectivity, background 4-connectivity (+ border background ~ outside).
+// One 32x32 tile per block, fully labelled in shared memory: run starts by warp ballot (horizontal
+// links cost nothing), vertical / diagonal links with the decision tree (one link per run overlap),
+// then every pixel's parent is written as the GLOBAL raster index of its tile-local root.
 __global__ void __launch_bounds__(256)
-ccl_merge1_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+ccl_local_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+  __shared__ int par[CCL_T * CCL_T];
+  __shared__ uint8_t m[CCL_T * CCL_T];
   const int n = blockIdx.z;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w || y >= h) return;
+  const int x0 = blockIdx.x * CCL_T, y0 = blockIdx.y * CCL_T;
+  const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
+  const uint8_t* gm = mask + (size_t)n * h * w;
+  const int gx = x0 + lx;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ly = ly0 + 8 * k, gy = y0 + ly;
+    const bool in = gx < w && gy < h;
+    const bool fg = in && gm[(size_t)gy * w + gx] != 0;
+    // pixels outside the image get class 2: they never match a real pixel
+    m[ly * CCL_T + lx] = in ? (fg ? 1 : 0) : 2;
+    const unsigned bits = __ballot_sync(0xffffffffu, fg);
+    const unsigned inb = __ballot_sync(0xffffffffu, in);
+    const unsigned same = fg ? bits : (in ? (~bits & inb) : ~inb);
+    const unsigned below = (~same) & ((1u << lx) - 1u);
+    const int start = below ? 32 - __clz(below) : 0;
+    par[ly * CCL_T + lx] = ly * CCL_T + start;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ly = ly0 + 8 * k;
+    if (ly == 0) continue;
+    const int p = ly * CCL_T + lx;
+    const int c = m[p];
+    if (c == 2) continue;
+    const bool hasW = lx > 0, hasE = lx < CCL_T - 1;
+    const bool N_ = m[p - CCL_T] == c;
+    if (c == 1) {
+      if (N_) {
+        if (!hasW || m[p - 1] != 1 || m[p - CCL_T - 1] != 1) suf_union(par, p, p - CCL_T);
+      } else {
+        if (hasE && m[p - CCL_T + 1] == 1) suf_union(par, p, p - CCL_T + 1);
+        if (hasW && m[p - CCL_T - 1] == 1) suf_union(par, p, p - CCL_T - 1);
+      }
+    } else if (N_ && (!hasW || m[p - 1] != 0 || m[p - CCL_T - 1] != 0)) {
+      suf_union(par, p, p - CCL_T);
+    }
+  }
+  __syncthreads();
+  int* gp = parent + (size_t)n * pstride;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ly = ly0 + 8 * k, gy = y0 + ly;
+    if (gx < w && gy < h) {
+      const int r = suf_find(par, ly * CCL_T + lx);
+      gp[(size_t)gy * w + gx] = (y0 + r / CCL_T) * w + x0 + (r % CCL_T);
+    }
+  }
+}
+
+// Boundary merge: global unions only for pixels on a tile border, towards their cross-tile neighbours
+// among {W, NW, N, NE} (foreground) or {W, N} (background).  Thread index enumerates the
+// border pixels: the first row of every tile row (y = 32k, k >= 1), then the first and last column
+// of every tile column for the remaining rows.
+__global__ void __launch_bounds__(256)
+ccl_border_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int h, int w, size_t pstride) {
+  const int n = blockIdx.y;
+  const int nrows = (h - 1) / CCL_T;                 // tile-row boundaries y = 32, 64, ...
+  const int ncols = (w - 1) / CCL_T;                 // tile-column boundaries x = 32, 64, ...
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int x, y;
+  bool row_border;
+  if (i < nrows * w) { y = (i / w + 1) * CCL_T; x = i % w; row_border = true; }
+  else {
+    const int j = i - nrows * w;
+    if (j >= ncols * 2 * h) return;
+    y = j % h;
+    const int cb = j / h;                            // 2 * boundary + side
+    x = (cb / 2 + 1) * CCL_T - (cb & 1);             // side 0: first column of the right tile; 1: last column of the left
+    row_border = false;
+    if ((y % CCL_T) == 0 && y > 0) return;           // already handled as a row-border pixel
+  }
   const uint8_t* m = mask + (size_t)n * h * w;
   int* par = parent + (size_t)n * pstride;
   const int p = y * w + x;
   const bool c = m[p] != 0;
   const bool hasW = x > 0, hasN = y > 0, hasE = x < w - 1;
-  // A vertical link is needed only at the first pixel of a run overlap: if W and NW are of my class and
-  // in my warp segment, then p~W and NW~N are implicit run links (ccl_init_kernel) and W~NW is W's job.
-  const bool seg0 = (x & 31) == 0;
-  if (c) {
-    // decision tree: a present N neighbour already touches W, NW and NE, so one link suffices
-    if (hasN && m[p - w] != 0) {
-      if (seg0 || m[p - 1] == 0 || m[p - w - 1] == 0) uf_union(par, p, p - w);
+  const bool tile_x0 = (x % CCL_T) == 0, tile_x31 = (x % CCL_T) == CCL_T - 1;
+  if (row_border) {
+    // N, NW, NE are all in the tile row above
+    if (c) {
+      if (m[p - w] != 0) {
+        // p~W and NW~N are tile-local links (if W, NW are in my tile column), W~NW is W's link
+        if (tile_x0 || m[p - 1] == 0 || m[p - w - 1] == 0) uf_union(par, p, p - w);
+      } else {
+        if (hasE && m[p - w + 1] != 0) uf_union(par, p, p - w + 1);
+        if (hasW && m[p - w - 1] != 0) uf_union(par, p, p - w - 1);
+      }
+      if (tile_x0 && hasW && m[p - 1] != 0) uf_union(par, p, p - 1);
     } else {
-      if (hasN && hasE && m[p - w + 1] != 0) uf_union(par, p, p - w + 1);
-      if (hasN && hasW && m[p - w - 1] != 0) uf_union(par, p, p - w - 1);
-      else if (hasW && seg0 && m[p - 1] != 0) uf_union(par, p, p - 1);
+      if (m[p - w] == 0 && (tile_x0 || m[p - 1] != 0 || m[p - w - 1] != 0)) uf_union(par, p, p - w);
+      if (tile_x0 && hasW && m[p - 1] == 0) uf_union(par, p, p - 1);
     }
-  } else {
-    if (hasN && m[p - w] == 0 && (seg0 || m[p - 1] != 0 || m[p - w - 1] != 0)) uf_union(par, p, p - w);
-    if (hasW && seg0 && m[p - 1] == 0) uf_union(par, p, p - 1);
+  } else if (tile_x0) {
+    // first column of a tile, not on a row border: W and NW are in the tile to the left
+    if (c) {
+      if (hasW && m[p - 1] != 0) uf_union(par, p, p - 1);
+      else if (hasW && hasN && m[p - w - 1] != 0) uf_union(par, p, p - w - 1);
+    } else if (hasW && m[p - 1] == 0) {
+      uf_union(par, p, p - 1);
+    }
+  } else if (tile_x31) {
+    // last column of a tile: only the NE diagonal crosses (E's own W-link covers p~E)
+    if (c && hasN && hasE && m[p - w + 1] != 0 && m[p - w] == 0 && m[p + 1] == 0) uf_union(par, p, p - w + 1);
   }
 }
 
