@@ -121,7 +121,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE configs[1])")
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"],
+                    help="configs[1] is quoted as fp32/TF32: tf32 tensor-core path by default")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-E training-step measurement")
