@@ -65,7 +65,8 @@ def test_variants(fml, n_classes, grey, precision):
     # float input = already preprocessed (Keras semantics), and raw uint8 without preprocessing
     xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
     got_f = eng.forward(xf, _lib.PREPROC_NONE)
-    assert np.abs(got_f - got).max() <= 1e-5
+    # (on the tensor-core path float input takes the FP32-pipe depthwise stem, uint8 the dense-L2 one)
+    assert np.abs(got_f - got).max() <= {"fp32": 1e-5, "tf32": 2e-2, "bf16": 1e-1}[precision]
     _check(eng, w, x, _lib.PREPROC_NONE, fml=fml, precision=precision)
 
 

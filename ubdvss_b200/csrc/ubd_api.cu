@@ -192,6 +192,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
     h->prof_dil = h->prof_stem = h->prof_ccl = h->prof_head = ubd_handle_s::Prof();
     for (double& v : h->host_ms) v = 0;
   }
+  else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
   else if (!strcmp(name, "tc_trace")) {
     if (value) { ENSURE(h->tc_trace, 3 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
     else if (h->tc_trace.p) { cudaFree(h->tc_trace.p); h->tc_trace.p = nullptr; h->tc_trace.cap = 0; }

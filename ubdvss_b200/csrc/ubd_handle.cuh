@@ -31,6 +31,7 @@ struct ubd_handle_s {
   bool have_weights = false;
   bool tc_weights_dirty = true;   // tensor-core weight images must be rebuilt from d_params
 
+  int opt_dense_l2 = 1;           // stem L2 as dense tensor-core conv for grey uint8 input (0: FP32-pipe depthwise path)
   int opt_chunk = 0;              // images per L2-resident chunk (0 = auto)
   int opt_max_comps = 4096;       // component slots per image
   int opt_max_points = 0;         // hull candidate capacity (0 = auto)
@@ -41,6 +42,7 @@ struct ubd_handle_s {
   int map_h = 0, map_w = 0, map_n = 0, map_prec = -1;     // shape the padded maps were last zeroed for
   DevBuf outer;
   DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
+  DevBuf l2dense;                 // merged dense 3x3 kernel of the stem's L2 (+ bias)
   DevBuf stem_wimg;               // pointwise B images of L2 / L3 for the tensor-core stem
   bool stem_weights_dirty = true;
   DevBuf tc_trace;                // optional event trace of CTA 0 (option "tc_trace")
@@ -54,7 +56,7 @@ struct ubd_handle_s {
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc_trace, &stem_wimg, &t_acts, &t_grads_act,
+            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
   }
 };

@@ -493,7 +493,11 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
   }
   const int p2 = stride2_pad(h);
   const bool mob = preproc == UBD_PREPROC_MOBILENET;
-  if (h->spec.cin == 1) {
+  if (h->spec.cin == 1 && in_dtype == UBD_U8 && h->opt_dense_l2) {
+    // L2 as a dense 3x3 conv on the tensor cores, L1 computed by producer warps of the same kernel
+    tc::L1Args la{mob ? h->d_lut : nullptr, h->d_params + h->spec.off[0], h->d_params + h->spec.off[1], h->d_params + h->spec.off[2], H, W, p2, p2};
+    rc = tc_launch_dilconv(h, d_img, act2, UBD_NLAYERS_DIL, n, H / 2, W / 2, 1, /*out_mode=*/1, /*out_pad=*/0, &la);
+  } else if (h->spec.cin == 1) {
     if (in_dtype == UBD_U8) rc = stem12_launch<1, uint8_t>(h, (const uint8_t*)d_img, act2, mob ? h->d_lut : nullptr, 0.f, 0.f, n, H, W, p2);
     else rc = stem12_launch<1, float>(h, (const float*)d_img, act2, nullptr, mob ? 127.5f : 0.f, 127.5f, n, H, W, p2);
   } else {

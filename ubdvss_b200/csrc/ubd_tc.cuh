@@ -68,8 +68,12 @@ struct Smem {
   uint64_t full[NS], empty[NS], tfull[NACC], tempty[NACC], wbar;
   uint32_t tmem_base;
   int abort_flag;
+  float lut[256];                // L1-producer variant: uint8 -> preprocessed float
+  float l1w[9 + UBD_NF + UBD_NF]; // dw1[9], pw1[24], b1[24] (grey input)
 };
-constexpr size_t SMEM_BYTES = sizeof(Smem) + 128;    // + manual 128 B alignment slack
+constexpr size_t SMEM_BYTES = sizeof(Smem) + 128;
+constexpr int L1_THREADS = 288;               // 9 warps: one thread per staged map pixel (sw + 2 = 258 are used)
+constexpr int THREADS_L1 = THREADS + L1_THREADS;    // + manual 128 B alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -185,11 +189,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // 6 planes of float4, bf16 maps 3 planes of 8 x bf16.  wb: this layer's B image followed by bias[32];
 // sw: strip width (128 or 256).  out_mode: 0 = same format as the input, tf32 output rounded (rna);
 // 1 = fp32 6-plane output without rounding (last layer, feeds the fp32 head).
-template <bool BF16>
-__global__ void __launch_bounds__(THREADS, 1)
+//
+// L1SRC variant (the stem's L2 layer as a dense conv, ubd_stem_tc.cuh): `in` is the uint8 grey IMAGE;
+// four extra warps compute layer L1 (separable s2 1->24, FP32, exact) for every staged row directly
+// into the slot ring (generic-proxy stores + fence.proxy.async + 128 mbarrier arrivals), so the L1 map
+// never exists in HBM.  h, w are then the half-resolution map size, d = 1.
+struct L1Args { const float* lut; const float* dw1; const float* pw1; const float* b1; int H, W, pad_t, pad_l; };
+
+template <bool BF16, bool L1SRC>
+__global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
 dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
-                  const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int out_mode, int* gerr,
-                  long long* trace) {
+                  const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad,
+                  int* gerr, long long* trace, L1Args l1) {
   constexpr int NGI = BF16 ? NG_BF16 : UBD_NG;                  // planes of the input map
   constexpr uint32_t WBB = BF16 ? WB_BYTES_BF16 : WB_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
@@ -203,7 +214,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
 #define TC_TRACE(role, slot, val) do { if (tr && tr_n < 1024) trace[((role) * 1024 + tr_n) * 4 + (slot)] = (val); } while (0)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), L1SRC ? L1_THREADS : 1); mbar_init(smem_u32(&S.empty[i]), 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&S.tfull[i]), 1); mbar_init(smem_u32(&S.tempty[i]), 4); }
     mbar_init(smem_u32(&S.wbar), 1);
     S.abort_flag = 0;
@@ -219,7 +230,8 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
   const Sched sched(n_imgs, h, w, d, sw);
   const uint32_t slots0 = smem_u32(S.slots);
-  const int wp = w + 2 * PAD;                              // global row pitch in pixels
+  const int wp = w + 2 * PAD;                              // global row pitch of the input map in pixels
+  const int wpo = w + 2 * out_pad;                         // ... of the output map
   const uint32_t plane_bytes = (uint32_t)(sw + 2 * PAD) * 16;   // slot plane stride = LBO
   const uint32_t slot_bytes = NGI * plane_bytes;
   const bool one_copy = (w == sw);                         // slot is an exact image of the global row block
@@ -231,7 +243,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
       bulk_g2s(smem_u32(S.wimg), wb, WBB, smem_u32(&S.wbar));
     }
     uint32_t lseq = 0;
-    bool ok = true;
+    bool ok = !L1SRC;                                      // L1SRC: the rows come from the L1 warps below
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
       Item it;
       if (!sched.get(idx, it)) continue;
@@ -337,6 +349,92 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
       }
       lbase += it.rows + 2;
     }
+  } else if (L1SRC && warp >= 7) {
+    // ------------------------------------------------------------------ L1 producers (9 warps)
+    // One thread = one map pixel of the staged row (only x in [x0-1, x0+sw] can be read by the d = 1
+    // taps).  The 9 image bytes of the NEXT row are loaded before waiting for its slot, so the global
+    // latency overlaps the wait and the previous row's arithmetic.
+    const int t = (int)threadIdx.x - THREADS;              // 0..287
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
+    for (int i = t; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
+    for (int i = t; i < 9 + 2 * UBD_NF; i += L1_THREADS) S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 9 + UBD_NF ? l1.pw1[i - 9] : l1.b1[i - 9 - UBD_NF]);
+    asm volatile("bar.sync 1, 288;" ::: "memory");         // the L1 warps only
+    float dwr[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dwr[i] = S.l1w[i];
+    // bytes of the 3x3 image patch of map pixel (yy, x); 0 where the tap is outside the image
+    auto load9 = [&](const uint8_t* irow, int yy, int x, uint32_t& valid, uint32_t b[3]) {
+      valid = 0u;
+#pragma unroll
+      for (int ti = 0; ti < 3; ++ti) {
+        b[ti] = 0u;
+        const int iy = 2 * yy - l1.pad_t + ti;
+#pragma unroll
+        for (int tj = 0; tj < 3; ++tj) {
+          const int ix = 2 * x - l1.pad_l + tj;
+          if (iy >= 0 && iy < l1.H && ix >= 0 && ix < l1.W) {
+            b[ti] |= (uint32_t)__ldg(irow + (size_t)iy * l1.W + ix) << (8 * tj);
+            valid |= 1u << (ti * 3 + tj);
+          }
+        }
+      }
+    };
+    auto l1_store = [&](uint8_t* sl, int i, bool inside, uint32_t valid, const uint32_t b[3]) {
+      float o[UBD_NF];
+      if (inside) {
+        float a = 0.f;
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+          for (int tj = 0; tj < 3; ++tj)
+            if (valid & (1u << (ti * 3 + tj))) a = fmaf(S.lut[(b[ti] >> (8 * tj)) & 255u], dwr[ti * 3 + tj], a);
+#pragma unroll
+        for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(fmaf(a, S.l1w[9 + c], S.l1w[9 + UBD_NF + c]), 0.f);
+      } else {
+#pragma unroll
+        for (int c = 0; c < UBD_NF; ++c) o[c] = 0.f;
+      }
+      uint8_t* px = sl + (size_t)(PAD - 1 + i) * 16;
+      if constexpr (BF16) {
+#pragma unroll
+        for (int g = 0; g < NG_BF16; ++g)
+          *reinterpret_cast<uint4*>(px + g * plane_bytes) =
+              make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                         pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+      } else {
+#pragma unroll
+        for (int g = 0; g < UBD_NG; ++g)
+          *reinterpret_cast<float4*>(px + g * plane_bytes) =
+              make_float4(round_tf32(o[4 * g]), round_tf32(o[4 * g + 1]), round_tf32(o[4 * g + 2]), round_tf32(o[4 * g + 3]));
+      }
+    };
+    uint32_t lseq = 0;
+    bool ok = true;
+    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
+      Item it;
+      if (!sched.get(idx, it)) continue;
+      const uint8_t* irow = img + ((size_t)it.n * l1.H) * l1.W;
+      const int x = it.x0 - 1 + t;                           // this thread's map column
+      const bool x_ok = x >= 0 && x < w && t < sw + 2;
+      uint32_t valid = 0u, b[3] = {0u, 0u, 0u};
+      int q = it.q0 - 1;
+      if (x_ok && q >= 0 && q < h) load9(irow, q, x, valid, b);
+      for (; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
+        const uint32_t slot = lseq % NS;
+        const bool row_ok = q >= 0 && q < h;                 // d = 1: phase row = map row
+        ok = mbar_wait(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 8);
+        if (!ok) break;
+        uint8_t* sl = S.slots + slot * slot_bytes;
+        // issue the next row's loads first, then do this row's arithmetic under their latency
+        const int qn = q + 1;
+        uint32_t nvalid = 0u, nb[3] = {0u, 0u, 0u};
+        if (qn <= it.q0 + it.rows && x_ok && qn >= 0 && qn < h) load9(irow, qn, x, nvalid, nb);
+        if (t < sw + 2) l1_store(sl, t, row_ok && x_ok, valid, b);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(smem_u32(&S.full[slot]));
+        valid = nvalid; b[0] = nb[0]; b[1] = nb[1]; b[2] = nb[2];
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
     const int quad = warp & 3;                              // TMEM lane quadrant this warp may read
@@ -389,19 +487,19 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
 #pragma unroll
             for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
             if (BF16 && out_mode == 0) {
-              uint4* o_px = out + (((size_t)it.n * h + y) * NG_BF16) * wp + PAD + x;
+              uint4* o_px = out + (((size_t)it.n * h + y) * NG_BF16) * wpo + out_pad + x;
 #pragma unroll
               for (int g = 0; g < NG_BF16; ++g)
-                o_px[(size_t)g * wp] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                o_px[(size_t)g * wpo] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
                                                   pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
             } else {
-              uint4* o_px = out + (((size_t)it.n * h + y) * UBD_NG) * wp + PAD + x;
+              uint4* o_px = out + (((size_t)it.n * h + y) * UBD_NG) * wpo + out_pad + x;
               const bool rnd = !BF16 && out_mode == 0;
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g) {
                 float4 q = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
                 if (rnd) { q.x = round_tf32(q.x); q.y = round_tf32(q.y); q.z = round_tf32(q.z); q.w = round_tf32(q.w); }
-                o_px[(size_t)g * wp] = *reinterpret_cast<uint4*>(&q);
+                o_px[(size_t)g * wpo] = *reinterpret_cast<uint4*>(&q);
               }
             }
           }
@@ -437,6 +535,16 @@ __global__ void build_wimg_kernel(const float* __restrict__ params, const int64_
   for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[W_BYTES / 4 + i] = i < UBD_NF ? B[i] : 0.f;
 }
 
+// K[tap][c][o] = dw[tap][c] * pw[c][o] (+ bias copy): a separable layer as one dense 3x3 kernel.
+__global__ void merge_sep_kernel(const float* __restrict__ dw, const float* __restrict__ pw, const float* __restrict__ b,
+                                 float* __restrict__ dst) {
+  for (int i = threadIdx.x; i < 9 * UBD_NF * UBD_NF; i += blockDim.x) {
+    const int tap = i / (UBD_NF * UBD_NF), c = (i / UBD_NF) % UBD_NF, o = i % UBD_NF;
+    dst[i] = dw[tap * UBD_NF + c] * pw[c * UBD_NF + o];
+  }
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[9 * UBD_NF * UBD_NF + i] = i < UBD_NF ? b[i] : 0.f;
+}
+
 // bf16 B images: per MMA [2 K cores][4 oc groups][8 oc rows][8 ic x bf16]; MMA list as in the kernel:
 // 0..8 = tap t, ic 0..15; 9..11 = row dy: core0 = tap (dy,-1) ic 16..23, core1 = tap (dy,0) ic 16..23;
 // 12..14 = row dy: core0 = tap (dy,+1) ic 16..23, core1 = 0.  Then the fp32 bias.
@@ -464,14 +572,26 @@ __global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const i
 }  // namespace tc
 
 static void tc_setup_attributes() {
-  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
 }
 
 // tc_weights buffer: [6 x WB_BYTES tf32 images][6 x WB_BYTES_BF16 bf16 images][zero page][err flag][offsets]
-static constexpr size_t kTcImgTf32 = (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES;
-static constexpr size_t kTcImgBf16 = (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16;
+static constexpr int kTcNumImg = UBD_NLAYERS_DIL + 1;            // + the stem's L2 as a merged dense 3x3 kernel
+static constexpr size_t kTcImgTf32 = (size_t)kTcNumImg * tc::WB_BYTES;
+static constexpr size_t kTcImgBf16 = (size_t)kTcNumImg * tc::WB_BYTES_BF16;
 static constexpr size_t kTcZeroOff = (kTcImgTf32 + kTcImgBf16 + 127) & ~(size_t)127;
+
+#define ENSURE_RAW(buf, bytes)                                                     \
+  do {                                                                             \
+    if ((buf).cap < (bytes)) {                                                     \
+      if ((buf).p) cudaFree((buf).p);                                              \
+      UBD_CUDA(cudaMalloc(&(buf).p, (bytes)));                                     \
+      (buf).cap = (bytes);                                                         \
+    }                                                                              \
+  } while (0)
 
 static int tc_prepare(ubd_handle h) {
   const size_t total = kTcZeroOff + tc::ZERO_BYTES + 256;
@@ -482,14 +602,23 @@ static int tc_prepare(ubd_handle h) {
     h->tc_weights_dirty = true;
   }
   if (h->tc_weights_dirty) {
-    int64_t offs[12];
+    int64_t offs[14];
     for (int l = 0; l < 6; ++l) { offs[l] = h->spec.off[9 + 2 * l]; offs[6 + l] = h->spec.off[10 + 2 * l]; }
+    offs[12] = 0; offs[13] = 9 * UBD_NF * UBD_NF;           // merged L2 kernel / bias inside h->l2dense
     int64_t* d_offs = reinterpret_cast<int64_t*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES + 64);
     UBD_CUDA(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, h->stream));
     UBD_CUDA(cudaStreamSynchronize(h->stream));      // offs is a stack array
     tc::build_wimg_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p);
     tc::build_wimg_bf16_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p + kTcImgTf32);
-    h->launches += 2;
+    // L2 (separable 24->24) as one dense 3x3 kernel: K[tap][c][o] = dw2[tap][c] * pw2[c][o], bias b2
+    ENSURE_RAW(h->l2dense, (9 * UBD_NF * UBD_NF + 32) * sizeof(float));
+    tc::merge_sep_kernel<<<1, 256, 0, h->stream>>>(h->d_params + h->spec.off[3], h->d_params + h->spec.off[4], h->d_params + h->spec.off[5],
+                                                   (float*)h->l2dense.p);
+    tc::build_wimg_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
+                                                    (uint8_t*)h->tc_weights.p + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES);
+    tc::build_wimg_bf16_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
+                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16);
+    h->launches += 5;
     UBD_CUDA(cudaGetLastError());
     h->tc_weights_dirty = false;
   }
@@ -501,9 +630,10 @@ static inline int* tc_err_flag(ubd_handle h) {
 }
 
 // in / out: padded maps in the precision's layout (tf32: 6 float4 planes, bf16: 3 planes of 8 bf16).
-// out_mode 1 writes fp32 6-plane output (last layer -> fp32 head).
+// out_mode 1 writes fp32 6-plane output (last layer -> fp32 head).  layer 0..5 = conv2d_1..6; layer 6 =
+// the stem's L2 as a dense conv with `in` = uint8 grey image and L1 computed by the producer warps.
 static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
-                             int out_mode) {
+                             int out_mode, int out_pad = UBD_MAP_PAD, const tc::L1Args* l1 = nullptr) {
   if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
   int rc = tc_prepare(h);
   if (rc) return rc;
@@ -516,12 +646,14 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
   const int n_chunks = ((hh + d - 1) / d + tc::RQ - 1) / tc::RQ;
   const long long items = (long long)n * n_strips * d * n_chunks;
   const int grid = (int)std::min<long long>(items, h->n_sm);
-  if (bf16)
-    tc::dilconv_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw,
-                                                                                 out_mode, tc_err_flag(h), (long long*)h->tc_trace.p);
-  else
-    tc::dilconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw,
-                                                                                  out_mode, tc_err_flag(h), (long long*)h->tc_trace.p);
+  tc::L1Args la{};
+  if (l1) la = *l1;
+#define UBD_TC_LAUNCH(BF, L1S, THR)                                                                                     \
+  tc::dilconv_tc_kernel<BF, L1S><<<grid, THR, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw, \
+                                                                           out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, la)
+  if (l1) { if (bf16) UBD_TC_LAUNCH(true, true, tc::THREADS_L1); else UBD_TC_LAUNCH(false, true, tc::THREADS_L1); }
+  else { if (bf16) UBD_TC_LAUNCH(true, false, tc::THREADS); else UBD_TC_LAUNCH(false, false, tc::THREADS); }
+#undef UBD_TC_LAUNCH
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
