@@ -350,7 +350,6 @@ static int ensure_maps(ubd_handle h, int n, int mh, int mw) {
   const bool grow = bytes > h->mapA.cap || bytes > h->mapB.cap;
   ENSURE(h->mapA, bytes);
   ENSURE(h->mapB, bytes);
-  if (h->precision == UBD_BF16) ENSURE(h->mapC, bytes);
   // the interior of one layout (fp32: 6 planes, bf16: 3 planes per row) overlaps the pads of the other
   if (grow || h->map_h != mh || h->map_w != mw || h->map_n < n || h->map_prec != h->precision) {
     UBD_CUDA(cudaMemsetAsync(h->mapA.p, 0, h->mapA.cap, h->stream));
@@ -410,16 +409,25 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
       const float* w = h->d_params + h->spec.off[9 + 2 * l];
       const float* b = h->d_params + h->spec.off[10 + 2 * l];
       const bool last = l == UBD_NLAYERS_DIL - 1;
-      float4* dst = (last && h->precision == UBD_BF16) ? (float4*)h->mapC.p : B;      // fp32 map for the head
-      if (h->precision == UBD_FP32) rc = launch_dil_fp32(h, A, B, w, b, nullptr, cn, h4, w4, kDilations[l], 0);
-      else rc = tc_launch_dilconv(h, A, dst, l, cn, h4, w4, kDilations[l], /*out_mode=*/last ? 1 : 0);
+      if (h->precision == UBD_FP32) {
+        rc = launch_dil_fp32(h, A, B, w, b, nullptr, cn, h4, w4, kDilations[l], 0);
+      } else if (last) {
+        // head + threshold fused into the last layer's epilogue (logits / mask straight from registers)
+        tc::HeadArgs ha{h->d_params + h->spec.off[21], h->d_params + h->spec.off[22], h->spec.n_out, thr,
+                        d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
+                        d_mask ? d_mask + (size_t)c0 * q_px : nullptr};
+        rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, UBD_MAP_PAD, nullptr, &ha);
+      } else {
+        rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0);
+      }
       if (rc) return rc;
       std::swap(A, B);
-      if (last && h->precision == UBD_BF16) A = dst;
     }
-    { ProfScope ps(h, &h->prof_head);
+    if (h->precision == UBD_FP32) {
+      ProfScope ps(h, &h->prof_head);
       rc = launch_head(h, A, d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
-                       d_mask ? d_mask + (size_t)c0 * q_px : nullptr, thr, cn, h4, w4); }
+                       d_mask ? d_mask + (size_t)c0 * q_px : nullptr, thr, cn, h4, w4);
+    }
     if (rc) return rc;
   }
   return UBD_OK;

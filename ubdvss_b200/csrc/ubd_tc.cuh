@@ -68,6 +68,7 @@ struct Smem {
   uint64_t full[NS], empty[NS], tfull[NACC], tempty[NACC], wbar;
   uint32_t tmem_base;
   int abort_flag;
+  float headw[UBD_NF * (1 + UBD_MAX_CLASSES) + 1 + UBD_MAX_CLASSES];   // out_mode 2: head kernel [24][n_out], bias
   float lut[256];                // L1-producer variant: uint8 -> preprocessed float
   float l1w[9 + UBD_NF + UBD_NF]; // dw1[9], pw1[24], b1[24] (grey input)
 };
@@ -194,13 +195,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // four extra warps compute layer L1 (separable s2 1->24, FP32, exact) for every staged row directly
 // into the slot ring (generic-proxy stores + fence.proxy.async + 128 mbarrier arrivals), so the L1 map
 // never exists in HBM.  h, w are then the half-resolution map size, d = 1.
+// out_mode 2: the 1x1 head (net.py:307-311) and the logit threshold (model_runner.py:124) run in the
+// epilogue: the thread that owns a pixel holds its 24 channels, so the last map never reaches HBM.
+struct HeadArgs { const float* hk; const float* hb; int n_out; float thr; float* logits; uint8_t* mask; };
 struct L1Args { const float* lut; const float* dw1; const float* pw1; const float* b1; int H, W, pad_t, pad_l; };
 
 template <bool BF16, bool L1SRC>
 __global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
 dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
                   const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad,
-                  int* gerr, long long* trace, L1Args l1) {
+                  int* gerr, long long* trace, L1Args l1, HeadArgs head) {
   constexpr int NGI = BF16 ? NG_BF16 : UBD_NG;                  // planes of the input map
   constexpr uint32_t WBB = BF16 ? WB_BYTES_BF16 : WB_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
@@ -444,6 +448,12 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
     for (int c = 0; c < UBD_NF; ++c)
       bias[c] = ok ? reinterpret_cast<const float*>(S.wimg + (BF16 ? W_BYTES_BF16 : W_BYTES))[c] : 0.f;
     uint32_t it_rows_plus2 = 0;
+    if (out_mode == 2) {
+      const int et = (int)threadIdx.x - 64;                  // 0..127 over the four epilogue warps
+      for (int i = et; i < UBD_NF * head.n_out; i += 128) S.headw[i] = head.hk[i];
+      for (int i = et; i < head.n_out; i += 128) S.headw[UBD_NF * head.n_out + i] = head.hb[i];
+      asm volatile("bar.sync 2, 128;" ::: "memory");         // the epilogue warps only
+    }
     uint32_t oseq = 0, lbase = 0;
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x, lbase += it_rows_plus2) {
       Item it;
@@ -486,7 +496,18 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
             float o[UBD_NF];
 #pragma unroll
             for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
-            if (BF16 && out_mode == 0) {
+            if (out_mode == 2) {
+              const size_t p = ((size_t)it.n * h + y) * w + x;
+              const float* hw = S.headw;
+              float* lo = head.logits ? head.logits + p * head.n_out : nullptr;
+              for (int oc = 0; oc < head.n_out; ++oc) {
+                float a = hw[UBD_NF * head.n_out + oc];
+#pragma unroll
+                for (int c = 0; c < UBD_NF; ++c) a = fmaf(o[c], hw[c * head.n_out + oc], a);
+                if (lo) lo[oc] = a;
+                if (oc == 0 && head.mask) head.mask[p] = a > head.thr ? 1 : 0;
+              }
+            } else if (BF16 && out_mode == 0) {
               uint4* o_px = out + (((size_t)it.n * h + y) * NG_BF16) * wpo + out_pad + x;
 #pragma unroll
               for (int g = 0; g < NG_BF16; ++g)
@@ -633,7 +654,8 @@ static inline int* tc_err_flag(ubd_handle h) {
 // out_mode 1 writes fp32 6-plane output (last layer -> fp32 head).  layer 0..5 = conv2d_1..6; layer 6 =
 // the stem's L2 as a dense conv with `in` = uint8 grey image and L1 computed by the producer warps.
 static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
-                             int out_mode, int out_pad = UBD_MAP_PAD, const tc::L1Args* l1 = nullptr) {
+                             int out_mode, int out_pad = UBD_MAP_PAD, const tc::L1Args* l1 = nullptr,
+                             const tc::HeadArgs* head = nullptr) {
   if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
   int rc = tc_prepare(h);
   if (rc) return rc;
@@ -648,9 +670,11 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
   const int grid = (int)std::min<long long>(items, h->n_sm);
   tc::L1Args la{};
   if (l1) la = *l1;
+  tc::HeadArgs ha{};
+  if (head) ha = *head;
 #define UBD_TC_LAUNCH(BF, L1S, THR)                                                                                     \
   tc::dilconv_tc_kernel<BF, L1S><<<grid, THR, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw, \
-                                                                           out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, la)
+                                                                           out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, la, ha)
   if (l1) { if (bf16) UBD_TC_LAUNCH(true, true, tc::THREADS_L1); else UBD_TC_LAUNCH(false, true, tc::THREADS_L1); }
   else { if (bf16) UBD_TC_LAUNCH(true, false, tc::THREADS); else UBD_TC_LAUNCH(false, false, tc::THREADS); }
 #undef UBD_TC_LAUNCH
