@@ -370,7 +370,14 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
   const int schunk = pick_stem_chunk(h, chunk, H, W);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
   if (h->precision == UBD_FP32) ENSURE(h->act1, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
-  ENSURE(h->act2, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
+  {
+    // plain layout, or split by column parity with x padding (tensor-core stem)
+    const size_t plain = (size_t)schunk * UBD_NG * half_px * sizeof(float4);
+    const size_t split = (size_t)schunk * (H / 2) * 2 * UBD_NG * (size_t)(W / 4 + 2 * UBD_MAP_PAD) * sizeof(float4);
+    const size_t cap0 = h->act2.cap;
+    ENSURE(h->act2, std::max(plain, split));
+    if (h->act2.cap != cap0) h->act2_tag = 0;
+  }
   { int rc_ = ensure_maps(h, chunk, h4, w4); if (rc_) return rc_; }
   const size_t img_stride = (size_t)H * W * h->spec.cin * (in_dtype == UBD_U8 ? 1 : 4);
   // 16-byte units per image of the L3 output map: 6 planes (fp32 / tf32) or 3 planes (bf16)

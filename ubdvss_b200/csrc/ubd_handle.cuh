@@ -39,7 +39,8 @@ struct ubd_handle_s {
   // inference workspaces
   DevBuf d_images, d_logits, d_mask;
   DevBuf act1, act2, mapA, mapB, mapC;     // mapC: fp32 output of the last layer in bf16 mode
-  int map_h = 0, map_w = 0, map_n = 0, map_prec = -1;     // shape the padded maps were last zeroed for
+  int map_h = 0, map_w = 0, map_n = 0, map_prec = -1;
+  long long act2_tag = 0;                  // geometry the parity-split act2 buffer was last zeroed for     // shape the padded maps were last zeroed for
   DevBuf outer;
   DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
   DevBuf l2dense;                 // merged dense 3x3 kernel of the stem's L2 (+ bias)

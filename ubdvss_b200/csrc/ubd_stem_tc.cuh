@@ -494,9 +494,21 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
   const int p2 = stride2_pad(h);
   const bool mob = preproc == UBD_PREPROC_MOBILENET;
   if (h->spec.cin == 1 && in_dtype == UBD_U8 && h->opt_dense_l2) {
-    // L2 as a dense 3x3 conv on the tensor cores, L1 computed by producer warps of the same kernel
+    // Whole stem on the tensor cores: L2 and L3 as dense 3x3 convs (merged separable kernels), L1 computed
+    // by producer warps of the L2 kernel.  act2 travels split by column parity so that L3's stride-2 taps
+    // are unit-stride descriptor offsets.
+    const int H2 = H / 2, W2 = W / 2;
+    const size_t split_bytes = (size_t)n * H2 * 2 * UBD_NG * (size_t)(W2 / 2 + 2 * UBD_MAP_PAD) * sizeof(float4);
+    const long long tag = ((long long)h->precision << 60) ^ ((long long)n << 40) ^ ((long long)H << 20) ^ (long long)W ^ (1LL << 59);
+    if (h->act2_tag != tag) {          // zero pads of the split layout: clear when the geometry / layout changes
+      UBD_CUDA(cudaMemsetAsync(act2, 0, std::min(split_bytes, h->act2.cap), h->stream));
+      h->act2_tag = tag;
+    }
     tc::L1Args la{mob ? h->d_lut : nullptr, h->d_params + h->spec.off[0], h->d_params + h->spec.off[1], h->d_params + h->spec.off[2], H, W, p2, p2};
-    rc = tc_launch_dilconv(h, d_img, act2, UBD_NLAYERS_DIL, n, H / 2, W / 2, 1, /*out_mode=*/1, /*out_pad=*/0, &la);
+    rc = tc_launch_dilconv(h, d_img, act2, UBD_NLAYERS_DIL, n, H2, W2, 1, /*out_mode=*/3, /*out_pad=*/UBD_MAP_PAD, &la);
+    if (rc) return rc;
+    return tc_launch_dilconv(h, act2, act3, UBD_NLAYERS_DIL + 1, n, H2 / 2, W2 / 2, 1, /*out_mode=*/0, UBD_MAP_PAD, nullptr, nullptr,
+                             /*s2=*/p2 ? 1 : 2);
   } else if (h->spec.cin == 1) {
     if (in_dtype == UBD_U8) rc = stem12_launch<1, uint8_t>(h, (const uint8_t*)d_img, act2, mob ? h->d_lut : nullptr, 0.f, 0.f, n, H, W, p2);
     else rc = stem12_launch<1, float>(h, (const float*)d_img, act2, nullptr, mob ? 127.5f : 0.f, 127.5f, n, H, W, p2);
@@ -505,6 +517,7 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
     else rc = stem12_launch<3, float>(h, (const float*)d_img, act2, nullptr, mob ? 127.5f : 0.f, 127.5f, n, H, W, p2);
   }
   if (rc) return rc;
+  h->act2_tag = 0;                     // plain-layout act2 from here on
   {
     const size_t smem = sizeof(stem::Smem3) + 128;
     static bool attr_set = false;

@@ -40,7 +40,7 @@ constexpr int SEG = 128;                      // pixels per MMA segment = UMMA M
 constexpr int MAX_SW = 256;                   // widest strip: two segments per staged row
 constexpr int PAD = UBD_MAP_PAD;              // 16 = largest dilation
 constexpr int MAX_PLANE_BYTES = (MAX_SW + 2 * PAD) * 16;        // 4608
-constexpr int MAX_SLOT_BYTES = UBD_NG * MAX_PLANE_BYTES;         // 27648
+constexpr int MAX_SLOT_BYTES = 30720;         // max(6 planes x 288 px, stride-2: 2 parities x 6 planes x 160 px) x 16 B
 constexpr int NS = 6;                         // row slots in the ring
 constexpr int NACC = 4;                       // TMEM accumulator stages
 constexpr int UMMA_N = 32;                    // 24 output channels padded to a legal N for M=128
@@ -204,8 +204,15 @@ template <bool BF16, bool L1SRC>
 __global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
 dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
                   const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad,
-                  int* gerr, long long* trace, L1Args l1, HeadArgs head) {
+                  int* gerr, long long* trace, L1Args l1, HeadArgs head, int s2) {
+  // s2 != 0: stride-2 conv (the stem's L3 as a dense conv).  The input map (2h rows) is stored split by
+  // column parity, [n][y][parity][plane][k + PAD] with E[k] = column 2k, O[k] = column 2k+1, so the tap
+  // (ti,tj) of output pixel x reads row 2y - pad + ti of array (tj - pad) & 1 at offset floor((tj - pad)/2):
+  // unit stride again, i.e. just another descriptor start address.  s2 = 1: pad 1 (FML), 2: pad 0.
+  const int s2pad = s2 == 1 ? 1 : 0;
+  const int rstep = s2 ? 2 : 1;                              // staged rows consumed per output row
   constexpr int NGI = BF16 ? NG_BF16 : UBD_NG;                  // planes of the input map
+  const int ngs = s2 ? 2 * NGI : NGI;                        // planes per staged row
   constexpr uint32_t WBB = BF16 ? WB_BYTES_BF16 : WB_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // keep the shared address space (no integer casts)
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -237,8 +244,8 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
   const int wp = w + 2 * PAD;                              // global row pitch of the input map in pixels
   const int wpo = w + 2 * out_pad;                         // ... of the output map
   const uint32_t plane_bytes = (uint32_t)(sw + 2 * PAD) * 16;   // slot plane stride = LBO
-  const uint32_t slot_bytes = NGI * plane_bytes;
-  const bool one_copy = (w == sw);                         // slot is an exact image of the global row block
+  const uint32_t slot_bytes = (uint32_t)ngs * plane_bytes;
+  const bool one_copy = (w == sw) && !s2;                         // slot is an exact image of the global row block
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -252,8 +259,9 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
       Item it;
       if (!sched.get(idx, it)) continue;
       const uint32_t copy_bytes = (uint32_t)it.copy_px * 16;
-      const uint32_t row_bytes = one_copy ? slot_bytes : NGI * copy_bytes;
-      for (int q = it.q0 - 1; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
+      const uint32_t row_bytes = one_copy ? slot_bytes : (uint32_t)ngs * copy_bytes;
+      const int nloads = s2 ? 2 * it.rows + 1 : it.rows + 2;
+      for (int li = 0; li < nloads && ok; ++li, ++lseq) {
         const uint32_t slot = lseq % NS;
         TC_TRACE(0, 0, clock64());
         ok = mbar_wait(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 1);
@@ -261,17 +269,20 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
         TC_TRACE(0, 1, clock64());
         const uint32_t bar = smem_u32(&S.full[slot]);
         const uint32_t dst = slots0 + slot * slot_bytes;
-        const bool valid = q >= 0 && q < it.nq;
-        // source of plane 0: padded pixel x0 of row y (the strip's left halo starts there)
-        const uint4* src = valid ? in + (((size_t)it.n * h + (it.r + q * d)) * NGI) * wp + it.x0
+        // input row: phase row q of the dilated walk, or row 2*q0 - pad + li of the stride-2 input
+        const int q = it.q0 - 1 + li;
+        const int yin = s2 ? 2 * it.q0 - s2pad + li : it.r + q * d;
+        const int hin = s2 ? 2 * h : h;
+        const bool valid = s2 ? (yin >= 0 && yin < hin) : (q >= 0 && q < it.nq);
+        // source of plane 0: padded pixel x0 of the row (the strip's left halo starts there)
+        const uint4* src = valid ? in + (((size_t)it.n * hin + yin) * ngs) * wp + it.x0
                                  : reinterpret_cast<const uint4*>(zeros);
         if (elect_one()) {
           mbar_expect_tx(bar, row_bytes);
           if (one_copy) {
             bulk_g2s(dst, src, slot_bytes, bar);
           } else {
-#pragma unroll
-            for (int g = 0; g < NGI; ++g)
+            for (int g = 0; g < ngs; ++g)
               bulk_g2s(dst + g * plane_bytes, valid ? src + (size_t)g * wp : src, copy_bytes, bar);
           }
         }
@@ -288,6 +299,24 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
     const uint32_t a_lbo = ((plane_bytes >> 4) & 0x3FFFu) << 16;
     // per-tap column offsets in 16-byte units: (PAD + dx*d) pixels, + K-pair (two planes)
     const uint32_t kp_units = (2 * plane_bytes) >> 4;
+    // per-tap column offset inside a staged row, in pixels (= 16-byte units), relative to PAD:
+    //   dilated:  tap dx -> dx * d
+    //   stride-2: tap tj -> parity array (tj - pad) & 1 (plane offset) and pixel offset floor((tj - pad) / 2)
+    uint32_t tap_off[3], pair_off, pair_lbo, single_off;
+    {
+      const uint32_t par_units = (uint32_t)NGI * (plane_bytes >> 4);
+#pragma unroll
+      for (int tj = 0; tj < 3; ++tj) {
+        if (s2) {
+          const int v = tj - s2pad;                                   // -1, 0, 1, 2
+          tap_off[tj] = (uint32_t)((v & 1) ? (int)par_units : 0) + (uint32_t)((v - (v & 1)) / 2);
+        } else {
+          tap_off[tj] = (uint32_t)((tj - 1) * d);
+        }
+      }
+      if (s2) { pair_off = tap_off[0]; pair_lbo = 1u; single_off = tap_off[1]; }      // taps tj = 0, 2 | tj = 1
+      else { pair_off = (uint32_t)(-d); pair_lbo = (uint32_t)d; single_off = (uint32_t)d; }   // dx = -1, 0 | dx = +1
+    }
     uint32_t lbase = 0, oseq = 0, waited = 0;      // waited = number of row loads known to have landed
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
       Item it;
@@ -296,7 +325,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
         for (int s = 0; s < it.nseg && ok; ++s, ++oseq) {
           if ((oseq & 1u) != parity) continue;
           if (parity == 0) TC_TRACE(1, 0, clock64());
-          while (waited < lbase + j + 3 && ok) {
+          while (waited < lbase + rstep * j + 3 && ok) {
             ok = mbar_wait(smem_u32(&S.full[waited % NS]), (waited / NS) & 1, abort_flag, gerr, 3);
             ++waited;
           }
@@ -311,13 +340,13 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
           uint32_t a_row[3];
 #pragma unroll
           for (int t = 0; t < 3; ++t)
-            a_row[t] = ((((slots0 + ((lbase + j + t) % NS) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo) + PAD;
+            a_row[t] = ((((slots0 + ((lbase + rstep * j + t) % NS) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo) + PAD;
           if (elect_one()) {
             if constexpr (!BF16) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const int dy = tap / 3, dx = tap % 3 - 1;
-                const uint32_t a_lo = a_row[dy] + (uint32_t)(s * SEG + dx * d);
+                const uint32_t a_lo = a_row[dy] + (uint32_t)(s * SEG) + tap_off[tap % 3];
 #pragma unroll
                 for (int kp = 0; kp < 3; ++kp) {
                   umma_tf32(tmem_d, make_desc(a_lo + kp * kp_units, DESC_HI),
@@ -329,19 +358,20 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
               const uint32_t lbo_mask = ~(0x3FFFu << 16);
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {                 // planes 0 + 1 of every tap
-                const int dy = tap / 3, dx = tap % 3 - 1;
-                umma_bf16(tmem_d, make_desc(a_row[dy] + (uint32_t)(s * SEG + dx * d), DESC_HI),
+                const int dy = tap / 3;
+                umma_bf16(tmem_d, make_desc(a_row[dy] + (uint32_t)(s * SEG) + tap_off[tap % 3], DESC_HI),
                           make_desc(b_lo0 + tap * (B_TILE_BYTES >> 4), DESC_HI), tap != 0);
               }
 #pragma unroll
               for (int dy = 0; dy < 3; ++dy) {
-                // plane 2 of taps dx = -1 (K core 0) and dx = 0 (K core 1): LBO = d pixels
+                // plane 2 of the two taps that are `pair_lbo` pixels apart in the same array (K cores 0, 1):
+                // dilated: dx = -1, 0 (LBO = d pixels); stride-2: tj = 0, 2 (same parity array, LBO = 1 pixel)
                 const uint32_t a2 = (a_row[dy] & lbo_mask) + 2 * plane_units + (uint32_t)(s * SEG);
-                umma_bf16(tmem_d, make_desc((a2 - d) | ((uint32_t)d << 16), DESC_HI),
+                umma_bf16(tmem_d, make_desc((a2 + pair_off) | (pair_lbo << 16), DESC_HI),
                           make_desc(b_lo0 + (9 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u);
-                // plane 2 of tap dx = +1; the B image's second K core is zero and LBO = 0 makes the A
+                // plane 2 of the remaining tap; the B image's second K core is zero and LBO = 0 makes the A
                 // side re-read the same (finite) core instead of whatever lies beyond the slot
-                umma_bf16(tmem_d, make_desc(a2 + d, DESC_HI),
+                umma_bf16(tmem_d, make_desc(a2 + single_off, DESC_HI),
                           make_desc(b_lo0 + (12 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u);
               }
             }
@@ -351,7 +381,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
           if (parity == 0) { TC_TRACE(1, 3, clock64()); ++tr_n; }
         }
       }
-      lbase += it.rows + 2;
+      lbase += s2 ? 2 * it.rows + 1 : it.rows + 2;
     }
   } else if (L1SRC && warp >= 7) {
     // ------------------------------------------------------------------ L1 producers (9 warps)
@@ -459,7 +489,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
       Item it;
       it_rows_plus2 = 0;
       if (!sched.get(idx, it)) continue;
-      it_rows_plus2 = it.rows + 2;
+      it_rows_plus2 = s2 ? 2 * it.rows + 1 : it.rows + 2;
       for (int j = 0; j < it.rows && ok; ++j) {
         const int y = it.r + (it.q0 + j) * d;
         for (int s = 0; s < it.nseg && ok; ++s, ++oseq) {
@@ -471,11 +501,9 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
           if (warp == 2 && lane == 0 && s == it.nseg - 1) {
             // every MMA of output rows <= j of this item has completed: the top row of the window
             // (and, after the item's last row, the two rows below it) can be overwritten
-            mbar_arrive(smem_u32(&S.empty[(lbase + j) % NS]));
-            if (j == it.rows - 1) {
-              mbar_arrive(smem_u32(&S.empty[(lbase + j + 1) % NS]));
-              mbar_arrive(smem_u32(&S.empty[(lbase + j + 2) % NS]));
-            }
+            for (int rr = 0; rr < rstep; ++rr) mbar_arrive(smem_u32(&S.empty[(lbase + rstep * j + rr) % NS]));
+            if (j == it.rows - 1)
+              for (int rr = rstep; rr < 3; ++rr) mbar_arrive(smem_u32(&S.empty[(lbase + rstep * j + rr) % NS]));
           }
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UMMA_N;
@@ -506,6 +534,24 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
                 for (int c = 0; c < UBD_NF; ++c) a = fmaf(o[c], hw[c * head.n_out + oc], a);
                 if (lo) lo[oc] = a;
                 if (oc == 0 && head.mask) head.mask[p] = a > head.thr ? 1 : 0;
+              }
+            } else if (out_mode == 3) {
+              // parity-split output in the precision's format (input of the stride-2 layer):
+              // [n][y][x & 1][plane][PAD + (x >> 1)], pitch w/2 + 2*PAD
+              constexpr int NGO = BF16 ? NG_BF16 : UBD_NG;
+              const size_t wps = (size_t)(w / 2 + 2 * PAD);
+              uint4* o_px = out + ((((size_t)it.n * h + y) * 2 + (x & 1)) * NGO) * wps + PAD + (x >> 1);
+              if constexpr (BF16) {
+#pragma unroll
+                for (int g = 0; g < NG_BF16; ++g)
+                  o_px[(size_t)g * wps] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                                                     pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+              } else {
+#pragma unroll
+                for (int g = 0; g < UBD_NG; ++g) {
+                  float4 q = make_float4(round_tf32(o[4 * g]), round_tf32(o[4 * g + 1]), round_tf32(o[4 * g + 2]), round_tf32(o[4 * g + 3]));
+                  o_px[(size_t)g * wps] = *reinterpret_cast<uint4*>(&q);
+                }
               }
             } else if (BF16 && out_mode == 0) {
               uint4* o_px = out + (((size_t)it.n * h + y) * NG_BF16) * wpo + out_pad + x;
@@ -570,7 +616,7 @@ __global__ void merge_sep_kernel(const float* __restrict__ dw, const float* __re
 // 0..8 = tap t, ic 0..15; 9..11 = row dy: core0 = tap (dy,-1) ic 16..23, core1 = tap (dy,0) ic 16..23;
 // 12..14 = row dy: core0 = tap (dy,+1) ic 16..23, core1 = 0.  Then the fp32 bias.
 __global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
-                                       const int64_t* __restrict__ boff, uint8_t* __restrict__ wimg_all) {
+                                       const int64_t* __restrict__ boff, uint8_t* __restrict__ wimg_all, int s2_pairing) {
   const int layer = blockIdx.x;
   const float* K = params + koff[layer];
   const float* B = params + boff[layer];
@@ -581,8 +627,8 @@ __global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const i
     const int oc = ngroup * 8 + row;
     int tap = -1, ic = 0;
     if (m < 9) { tap = m; ic = kcore * 8 + col; }
-    else if (m < 12) { tap = (m - 9) * 3 + kcore; ic = 16 + col; }            // dx = -1 (core 0), dx = 0 (core 1)
-    else if (kcore == 0) { tap = (m - 12) * 3 + 2; ic = 16 + col; }           // dx = +1
+    else if (m < 12) { tap = (m - 9) * 3 + (s2_pairing ? 2 * kcore : kcore); ic = 16 + col; }   // cores 0,1 = dx -1,0 | tj 0,2
+    else if (kcore == 0) { tap = (m - 12) * 3 + (s2_pairing ? 1 : 2); ic = 16 + col; }          // dx = +1 | tj = 1
     const float v = (tap >= 0 && oc < UBD_NF) ? K[(tap * UBD_NF + ic) * UBD_NF + oc] : 0.f;
     dst[i] = __float2bfloat16_rn(v);
   }
@@ -600,7 +646,7 @@ static void tc_setup_attributes() {
 }
 
 // tc_weights buffer: [6 x WB_BYTES tf32 images][6 x WB_BYTES_BF16 bf16 images][zero page][err flag][offsets]
-static constexpr int kTcNumImg = UBD_NLAYERS_DIL + 1;            // + the stem's L2 as a merged dense 3x3 kernel
+static constexpr int kTcNumImg = UBD_NLAYERS_DIL + 2;            // + the stem's L2 and L3 as merged dense 3x3 kernels
 static constexpr size_t kTcImgTf32 = (size_t)kTcNumImg * tc::WB_BYTES;
 static constexpr size_t kTcImgBf16 = (size_t)kTcNumImg * tc::WB_BYTES_BF16;
 static constexpr size_t kTcZeroOff = (kTcImgTf32 + kTcImgBf16 + 127) & ~(size_t)127;
@@ -630,16 +676,23 @@ static int tc_prepare(ubd_handle h) {
     UBD_CUDA(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, h->stream));
     UBD_CUDA(cudaStreamSynchronize(h->stream));      // offs is a stack array
     tc::build_wimg_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p);
-    tc::build_wimg_bf16_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p + kTcImgTf32);
+    tc::build_wimg_bf16_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p + kTcImgTf32, 0);
     // L2 (separable 24->24) as one dense 3x3 kernel: K[tap][c][o] = dw2[tap][c] * pw2[c][o], bias b2
-    ENSURE_RAW(h->l2dense, (9 * UBD_NF * UBD_NF + 32) * sizeof(float));
+    ENSURE_RAW(h->l2dense, 2 * (9 * UBD_NF * UBD_NF + 32) * sizeof(float));
     tc::merge_sep_kernel<<<1, 256, 0, h->stream>>>(h->d_params + h->spec.off[3], h->d_params + h->spec.off[4], h->d_params + h->spec.off[5],
                                                    (float*)h->l2dense.p);
     tc::build_wimg_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
                                                     (uint8_t*)h->tc_weights.p + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES);
     tc::build_wimg_bf16_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
-                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16);
-    h->launches += 5;
+                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16, 0);
+    // L3 (separable 24->24, stride 2) likewise, image index 7
+    float* l3 = (float*)h->l2dense.p + (9 * UBD_NF * UBD_NF + 32);
+    tc::merge_sep_kernel<<<1, 256, 0, h->stream>>>(h->d_params + h->spec.off[6], h->d_params + h->spec.off[7], h->d_params + h->spec.off[8], l3);
+    tc::build_wimg_kernel<<<1, 256, 0, h->stream>>>(l3, d_offs + 12, d_offs + 13,
+                                                    (uint8_t*)h->tc_weights.p + (size_t)(UBD_NLAYERS_DIL + 1) * tc::WB_BYTES);
+    tc::build_wimg_bf16_kernel<<<1, 256, 0, h->stream>>>(l3, d_offs + 12, d_offs + 13,
+                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)(UBD_NLAYERS_DIL + 1) * tc::WB_BYTES_BF16, 1);
+    h->launches += 8;
     UBD_CUDA(cudaGetLastError());
     h->tc_weights_dirty = false;
   }
@@ -655,7 +708,7 @@ static inline int* tc_err_flag(ubd_handle h) {
 // the stem's L2 as a dense conv with `in` = uint8 grey image and L1 computed by the producer warps.
 static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
                              int out_mode, int out_pad = UBD_MAP_PAD, const tc::L1Args* l1 = nullptr,
-                             const tc::HeadArgs* head = nullptr) {
+                             const tc::HeadArgs* head = nullptr, int s2 = 0) {
   if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
   int rc = tc_prepare(h);
   if (rc) return rc;
@@ -663,7 +716,7 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
   const uint8_t* base = (const uint8_t*)h->tc_weights.p;
   const uint8_t* wb = bf16 ? base + kTcImgTf32 + (size_t)layer * tc::WB_BYTES_BF16 : base + (size_t)layer * tc::WB_BYTES;
   const uint8_t* zeros = base + kTcZeroOff;
-  const int sw = ww <= tc::SEG ? tc::SEG : tc::MAX_SW;
+  const int sw = (ww <= tc::SEG || s2) ? tc::SEG : tc::MAX_SW;      // stride-2 rows stage both parities: 128-px strips
   const int n_strips = (ww + sw - 1) / sw;
   const int n_chunks = ((hh + d - 1) / d + tc::RQ - 1) / tc::RQ;
   const long long items = (long long)n * n_strips * d * n_chunks;
@@ -674,7 +727,7 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
   if (head) ha = *head;
 #define UBD_TC_LAUNCH(BF, L1S, THR)                                                                                     \
   tc::dilconv_tc_kernel<BF, L1S><<<grid, THR, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw, \
-                                                                           out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, la, ha)
+                                                                           out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, la, ha, s2)
   if (l1) { if (bf16) UBD_TC_LAUNCH(true, true, tc::THREADS_L1); else UBD_TC_LAUNCH(false, true, tc::THREADS_L1); }
   else { if (bf16) UBD_TC_LAUNCH(true, false, tc::THREADS); else UBD_TC_LAUNCH(false, false, tc::THREADS); }
 #undef UBD_TC_LAUNCH
