@@ -44,35 +44,100 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed regions (B200_PROFILING.md).  A thread polls NVML
+    (nvidia_ml_py) every ~2 ms from before the warm-up until after the end-to-end loop; `mark()` brackets
+    the timed regions so that `sm_mhz` is the median over samples taken inside them.  Falls back to one
+    background `nvidia-smi -lms 100` process when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.proc, self.rows = index, None, []
+        self.samples, self.windows, self._t0 = [], [], None       # (t, sm_mhz, reasons_bitmask, power_w)
+        self.nvml, self.thread, self.stop = None, None, False
+        self.sm_max = None
 
-    def _run(self):
-        while not self._stop.is_set():
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            time.sleep(0.002)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True); self._t.start(); return self
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.replace(",", "").isdigit() else self.index
+            self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            self.nvml = nv
+            import threading
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            except Exception:
+                self.proc = None
+        return self
+
+    def mark(self, begin):
+        """Bracket a timed region (wall clock; the regions are synchronised on both sides)."""
+        if begin:
+            self._t0 = time.perf_counter()
+        elif self._t0 is not None:
+            self.windows.append((self._t0, time.perf_counter()))
+            self._t0 = None
 
     def __exit__(self, *a):
-        self._stop.set(); self._t.join(timeout=6)
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.count(",") >= 8]
+
+    def _summary_nvml(self):
+        nv = self.nvml
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+        pmax = max((s[3] for s in self.samples), default=0.0)
+        loaded = inside if inside else [s for s in self.samples if s[3] >= 0.5 * pmax]
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, v in bits.items() if any(s[2] & v for s in loaded))
+        return {"sm_mhz": statistics.median(s[1] for s in loaded) if loaded else None, "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(self.samples), "samples_in_timed_regions": len(inside),
+                "power_w_max": pmax, "source": "nvml"}
 
     def summary(self):
+        if self.nvml is not None and self.samples:
+            return self._summary_nvml()
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        power = [num(r[3]) for r in self.rows]
+        sm_all = [num(r[1]) for r in self.rows]
+        # "under load": samples drawing more than half of the highest power seen
+        pmax = max([p for p in power if p is not None], default=0.0)
+        sm = [s for s, p in zip(sm_all, power) if s is not None and (p is None or p >= 0.5 * pmax)]
+        mx = [num(r[2]) for r in self.rows if num(r[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -80,7 +145,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "samples_under_load": len(sm),
+                "power_w_max": pmax, "source": "nvidia-smi"}
 
 
 def make_images(batch, size, seed=1):
@@ -194,18 +260,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local_rank)
+    clk.__enter__()
     for _ in range(args.warmup):
         comps, counts = step_dev()
     eng.set_option("profile", 1)
     barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        e0.record(stream)
-        for _ in range(args.steps):
-            comps, counts = step_dev()
-        e1.record(stream)
-        barrier()
+    clk.mark(True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        comps, counts = step_dev()
+    e1.record(stream)
+    barrier()
+    clk.mark(False)
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
     dil_ms, dil_n = eng.stat("dilconv_ms"), eng.stat("dilconv_launches")
@@ -228,12 +297,15 @@ def main():
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
+    clk.mark(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         counts_h = step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clk.mark(False)
     n_comp_last = int(counts_h.sum())
+    clk.__exit__()
 
     # config E beside it: training step (forward + loss + backward + Adam) on 32 x 512x512 per GPU,
     # gradients all-reduced over NCCL when N > 1 (the only collective on the path)
@@ -279,8 +351,14 @@ def main():
         avg_launch_s = dil_ms / 1e3 / max(dil_n, 1)
         achieved_tf = flops_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
         peak_tf = pk["bf16_tflops_sustained"] * (0.5 if args.precision in ("fp32", "tf32") else 1.0)
+        traffic = None
+        try:    # dram bytes of one dilated-layer launch from the committed `ncu --set full` capture
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))[args.precision]
+            traffic = tj["dram_bytes_per_launch"] * imgs_per_launch * (S * S / 1048576.0) / tj["images_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "dilated 3x3 conv 24->24 (L4-L9)", "achieved": achieved_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                 "peak_source": f"{pk['source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s"
                                + (" x 0.5 (tf32 rate)" if args.precision in ("fp32", "tf32") else ""),
                 "avg_launch_us": avg_launch_s * 1e6, "launches": int(dil_n),
