@@ -179,7 +179,31 @@ def time_cpu(weights, images_u8, thr, steps, warmup):
     return images_u8.shape[0] * steps / dt, dt / steps, cores
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (NCCL's version banner, torchrun notices) goes to stderr: fd 1 is pointed at fd 2 and
+    the ONE JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -222,7 +246,7 @@ def main():
                                            "restatement of net.py + the reference's cv2 post-processing; TF/Keras absent)"},
                 "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -383,7 +407,7 @@ def main():
             v, step_s, cores = time_cpu(weights, imgs[:args.cpu_sample], thr, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
                                     "sample": f"3 steps x {args.cpu_sample} images of {S}x{S} (torch-CPU restatement + cv2)"}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
