@@ -26,7 +26,7 @@ def _ref_layer(w, x, layer, tf32):
 
 
 @pytest.mark.parametrize("layer", range(6))
-@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 32, 256), (3, 20, 36), (1, 136, 240), (1, 4, 4)])
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 32, 256), (3, 20, 36), (1, 136, 240), (1, 4, 4), (12, 64, 64), (3, 160, 528)])
 def test_tf32_layer_matches_fp32_and_oracle(eng, layer, shape):
     rng = np.random.default_rng(layer * 10 + shape[1])
     # post-ReLU-like input on the tf32 grid, as the producing kernel's epilogue (cvt.rna) leaves it
@@ -62,7 +62,7 @@ def _round_bf16(a):
 
 
 @pytest.mark.parametrize("layer", range(6))
-@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 32, 256), (3, 20, 36), (1, 136, 240)])
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 32, 256), (3, 20, 36), (1, 136, 240), (12, 64, 64), (3, 160, 528)])
 def test_bf16_layer_matches_oracle(eng, layer, shape):
     """kind::f16 (bf16 operands, fp32 accumulate): against the oracle evaluated on bf16-rounded inputs and
     weights only the fp32 accumulation order remains."""

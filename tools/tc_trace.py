@@ -9,17 +9,18 @@ from ubdvss_b200 import _lib
 
 layer = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-eng = Engine(precision="tf32")
+prec = sys.argv[3] if len(sys.argv) > 3 else "tf32"
+eng = Engine(precision=prec)
 eng.set_weights(onet.init_weights(0, seed=1234))
 x = np.maximum(np.random.default_rng(0).normal(0, 1, size=(n, 256, 256, 24)), 0).astype(np.float32)
-eng.debug_dilated_layer(x, layer, "tf32")          # warm-up (weights image, allocations)
+eng.debug_dilated_layer(x, layer, prec)          # warm-up (weights image, allocations)
 eng.set_option("tc_trace", 1)
-eng.debug_dilated_layer(x, layer, "tf32")
-tr = np.zeros((3, 1024, 4), np.int64)
+eng.debug_dilated_layer(x, layer, prec)
+tr = np.zeros((4, 1024, 4), np.int64)
 _lib.check(eng.handle, eng._lib.ubd_debug_read_trace(eng.handle, _lib.ptr(tr), tr.size))
-t0 = min(tr[r, 0, 0] for r in range(3) if tr[r, 0, 0] > 0)
-names = ["producer: wait_start wait_end issued", "mma: row_start seg_start tempty_ok issued", "epilogue(w2): wait_start tfull_ok stored"]
-for r in range(3):
+t0 = min(tr[r, 0, 0] for r in range(4) if tr[r, 0, 0] > 0)
+names = ["producer: wait_start wait_end issued", "mma: row_start gempty_ok full_ok issued", "drainer q0: wait_start gfull+dump_ok loaded rearmed", "finisher w2: wait_start dfull_ok stored"]
+for r in range(4):
     ev = tr[r]
     k = int((ev[:, 0] > 0).sum())
     print(f"== role {r} ({names[r]}), {k} events")

@@ -15,6 +15,7 @@
 #include "ubd_fp32.cuh"
 #include "ubd_handle.cuh"
 #include "ubd_tc.cuh"
+#include "ubd_tc3.cuh"
 #include "ubd_stem_tc.cuh"
 #include "ubd_train.cuh"
 
@@ -128,6 +129,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
   cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
   tc_setup_attributes();
+  tc3_setup_attributes();
   *out = h;
   return UBD_OK;
 }
@@ -193,8 +195,9 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
     for (double& v : h->host_ms) v = 0;
   }
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
+  else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
   else if (!strcmp(name, "tc_trace")) {
-    if (value) { ENSURE(h->tc_trace, 3 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
+    if (value) { ENSURE(h->tc_trace, 4 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
     else if (h->tc_trace.p) { cudaFree(h->tc_trace.p); h->tc_trace.p = nullptr; h->tc_trace.cap = 0; }
   }
   else if (!strcmp(name, "precision")) { if (value < UBD_FP32 || value > UBD_BF16) UBD_FAIL(UBD_ERR_ARG, "bad precision"); h->precision = (int)value; }
@@ -226,6 +229,7 @@ extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const i
   UBD_CUDA(cudaStreamSynchronize(h->stream));
   h->have_weights = true;
   h->tc_weights_dirty = true;
+  h->tc3_weights_dirty = true;
   h->stem_weights_dirty = true;
   return UBD_OK;
 }
@@ -423,9 +427,11 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
         tc::HeadArgs ha{h->d_params + h->spec.off[21], h->d_params + h->spec.off[22], h->spec.n_out, thr,
                         d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
                         d_mask ? d_mask + (size_t)c0 * q_px : nullptr};
-        rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, UBD_MAP_PAD, nullptr, &ha);
+        rc = h->opt_tc_variant ? tc3_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, UBD_MAP_PAD, &ha)
+                               : tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, UBD_MAP_PAD, nullptr, &ha);
       } else {
-        rc = tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0);
+        rc = h->opt_tc_variant ? tc3_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0)
+                               : tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0);
       }
       if (rc) return rc;
       std::swap(A, B);
@@ -730,7 +736,8 @@ extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float
   } else {
     const int saved = h->precision;
     h->precision = precision;
-    rc = tc_launch_dilconv(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1);
+    rc = h->opt_tc_variant ? tc3_launch_dilconv(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1)
+                           : tc_launch_dilconv(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1);
     h->precision = saved;
   }
   if (rc) return rc;
@@ -744,7 +751,7 @@ extern "C" int ubd_debug_read_trace(ubd_handle h, long long* out, int n_values) 
   if (!h || !out || !h->tc_trace.p) return UBD_ERR_ARG;
   UBD_CUDA(cudaSetDevice(h->device));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
-  UBD_CUDA(cudaMemcpy(out, h->tc_trace.p, std::min<size_t>((size_t)n_values * 8, 3 * 1024 * 4 * 8), cudaMemcpyDeviceToHost));
+  UBD_CUDA(cudaMemcpy(out, h->tc_trace.p, std::min<size_t>((size_t)n_values * 8, 4 * 1024 * 4 * 8), cudaMemcpyDeviceToHost));
   UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap));
   return UBD_OK;
 }

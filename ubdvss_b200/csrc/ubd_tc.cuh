@@ -739,12 +739,15 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
 // Reads (and clears) the device-side barrier-timeout flag; call after a stream synchronize.
 static int tc_check_error(ubd_handle h) {
   if (!h->tc_weights.p) return UBD_OK;
-  int code = 0;
-  UBD_CUDA(cudaMemcpyAsync(&code, tc_err_flag(h), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int codes[16] = {0};
+  UBD_CUDA(cudaMemcpyAsync(codes, tc_err_flag(h), sizeof(codes), cudaMemcpyDeviceToHost, h->stream));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
-  if (code) {
-    cudaMemsetAsync(tc_err_flag(h), 0, sizeof(int), h->stream);
-    UBD_FAIL(UBD_ERR_CUDA, "tcgen05 pipeline barrier timed out (role code " + std::to_string(code) + ")");
+  if (codes[0]) {
+    cudaMemsetAsync(tc_err_flag(h), 0, sizeof(codes), h->stream);
+    std::string where;
+    for (int i = 1; i < 16; ++i)
+      if (codes[i]) where += " w" + std::to_string(i - 1) + ":" + std::to_string(codes[i] >> 24) + "/" + std::to_string(codes[i] & 0xFFFFFF);
+    UBD_FAIL(UBD_ERR_CUDA, "tcgen05 pipeline barrier timed out (role code " + std::to_string(codes[0]) + ";" + where + ")");
   }
   return UBD_OK;
 }
