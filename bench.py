@@ -260,6 +260,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     eng = Engine(device=local_rank, precision=args.precision)
     eng.set_weights(weights)
+    for opt in ("tc_variant", "dense_l2"):
+        if os.environ.get("UBD_" + opt.upper()):
+            eng.set_option(opt, int(os.environ["UBD_" + opt.upper()]))
     if os.environ.get("UBD_CHUNK"):
         eng.set_option("chunk", int(os.environ["UBD_CHUNK"]))
     B, S = args.batch, args.size

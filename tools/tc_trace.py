@@ -14,12 +14,13 @@ eng = Engine(precision=prec)
 eng.set_weights(onet.init_weights(0, seed=1234))
 x = np.maximum(np.random.default_rng(0).normal(0, 1, size=(n, 256, 256, 24)), 0).astype(np.float32)
 eng.debug_dilated_layer(x, layer, prec)          # warm-up (weights image, allocations)
+if len(sys.argv) > 4: eng.set_option('tc_variant', int(sys.argv[4]))
 eng.set_option("tc_trace", 1)
 eng.debug_dilated_layer(x, layer, prec)
 tr = np.zeros((4, 1024, 4), np.int64)
 _lib.check(eng.handle, eng._lib.ubd_debug_read_trace(eng.handle, _lib.ptr(tr), tr.size))
 t0 = min(tr[r, 0, 0] for r in range(4) if tr[r, 0, 0] > 0)
-names = ["producer: wait_start wait_end issued", "mma: row_start gempty_ok full_ok issued", "drainer q0: wait_start gfull+dump_ok loaded rearmed", "finisher w2: wait_start dfull_ok stored"]
+names = ["producer: wait_start wait_end issued", "mma: row_start gempty_ok full_ok issued", "epilogue seg0 q0: wait_start gfull_ok rearmed stored", "-"]
 for r in range(4):
     ev = tr[r]
     k = int((ev[:, 0] > 0).sum())

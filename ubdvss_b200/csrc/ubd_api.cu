@@ -15,7 +15,7 @@
 #include "ubd_fp32.cuh"
 #include "ubd_handle.cuh"
 #include "ubd_tc.cuh"
-#include "ubd_tc3.cuh"
+#include "ubd_tc4.cuh"
 #include "ubd_stem_tc.cuh"
 #include "ubd_train.cuh"
 
@@ -129,7 +129,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
   cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
   tc_setup_attributes();
-  tc3_setup_attributes();
+  tc4_setup_attributes();
   *out = h;
   return UBD_OK;
 }
@@ -229,7 +229,7 @@ extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const i
   UBD_CUDA(cudaStreamSynchronize(h->stream));
   h->have_weights = true;
   h->tc_weights_dirty = true;
-  h->tc3_weights_dirty = true;
+  h->tc4_weights_dirty = true;
   h->stem_weights_dirty = true;
   return UBD_OK;
 }
@@ -327,6 +327,14 @@ static int launch_head(ubd_handle h, const float4* in, float* logits, uint8_t* m
   head_threshold_kernel<<<grid, block, 0, h->stream>>>(in, logits, mask, hk, hb, h->spec.n_out, thr, n, hh, ww, UBD_MAP_PAD);
   LAUNCH_CHECK();
   return UBD_OK;
+}
+
+// Dilated layer on the tensor cores: 1 = column-rotating kernel (ubd_tc4.cuh, default), 0 = one output row
+// per accumulator (ubd_tc.cuh); option "tc_variant".
+static int launch_dil_tc(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d, int out_mode,
+                         const tc::HeadArgs* head = nullptr) {
+  if (h->opt_tc_variant) return tc4_launch_dilconv(h, in, out, layer, n, hh, ww, d, out_mode, UBD_MAP_PAD, head);
+  return tc_launch_dilconv(h, in, out, layer, n, hh, ww, d, out_mode, UBD_MAP_PAD, nullptr, head);
 }
 
 // Images per sweep of the dilated layers / head ("chunk") and per stem launch ("stem chunk").
@@ -427,11 +435,9 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
         tc::HeadArgs ha{h->d_params + h->spec.off[21], h->d_params + h->spec.off[22], h->spec.n_out, thr,
                         d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
                         d_mask ? d_mask + (size_t)c0 * q_px : nullptr};
-        rc = h->opt_tc_variant ? tc3_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, UBD_MAP_PAD, &ha)
-                               : tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, UBD_MAP_PAD, nullptr, &ha);
+        rc = launch_dil_tc(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/2, &ha);
       } else {
-        rc = h->opt_tc_variant ? tc3_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0)
-                               : tc_launch_dilconv(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0);
+        rc = launch_dil_tc(h, A, B, l, cn, h4, w4, kDilations[l], /*out_mode=*/0);
       }
       if (rc) return rc;
       std::swap(A, B);
@@ -736,8 +742,7 @@ extern "C" int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float
   } else {
     const int saved = h->precision;
     h->precision = precision;
-    rc = h->opt_tc_variant ? tc3_launch_dilconv(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1)
-                           : tc_launch_dilconv(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1);
+    rc = launch_dil_tc(h, h->mapA.p, h->mapB.p, layer, n, mh, mw, kDilations[layer], /*out_mode=*/1);
     h->precision = saved;
   }
   if (rc) return rc;

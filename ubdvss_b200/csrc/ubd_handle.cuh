@@ -30,8 +30,8 @@ struct ubd_handle_s {
   float* d_lut = nullptr;         // uint8 -> mobilenet_like preprocessing table
   bool have_weights = false;
   bool tc_weights_dirty = true;   // tensor-core weight images must be rebuilt from d_params
-  bool tc3_weights_dirty = true;  // ... the row-rotating kernel's A images (ubd_tc3.cuh)
-  int opt_tc_variant = 1;         // dilated layers: 1 = row-rotating kernel (ubd_tc3.cuh), 0 = pixel-major kernel (ubd_tc.cuh)
+  bool tc4_weights_dirty = true;  // ... the column-rotating kernel's weight images (ubd_tc4.cuh)
+  int opt_tc_variant = 1;         // dilated layers: 1 = ubd_tc4.cuh, 0 = ubd_tc.cuh (see launch_dil_tc)
 
   int opt_dense_l2 = 1;           // stem L2 as dense tensor-core conv for grey uint8 input (0: FP32-pipe depthwise path)
   int opt_chunk = 0;              // images per L2-resident chunk (0 = auto)
@@ -50,7 +50,7 @@ struct ubd_handle_s {
   bool stem_weights_dirty = true;
   DevBuf tc_trace;                // optional event trace of CTA 0 (option "tc_trace")
   DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
-  DevBuf tc3_weights;             // per-layer UMMA A-operand images of the row-rotating kernel (+ bias)
+  DevBuf tc4_weights;             // per-layer weight images of the column-rotating kernel (+ bias)
   // training workspaces
   DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss;
   int64_t adam_t = 0;
@@ -60,7 +60,7 @@ struct ubd_handle_s {
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc3_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
+            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
   }
 };

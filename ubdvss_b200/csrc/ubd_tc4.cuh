@@ -1,0 +1,506 @@
+// Dilated 3x3 24->24 layers (net.py:298-304) on tcgen05, "column-rotating" formulation, sm_100a only.
+//
+// Pixels stay on the M side as in ubd_tc.cuh (D[128 px, N], lane = pixel, so the epilogue owns all 24
+// channels of its pixel and all four TMEM quadrants drain in parallel), but the three kernel rows share
+// one instruction through the N side:
+//
+//   D[128 px, 96 = (ky2 | ky1 | ky0) x 32 oc]  +=  A[128 px, K] (one staged map row)  *  B[K, 96] (weights)
+//
+// An input row r of a y-phase (rows c, c+d, c+2d, ...) contributes to the output rows r-1, r, r+1 through
+// the kernel rows ky = 2, 1, 0.  A segment's accumulator tile has four 32-column groups; output row o owns
+// group o mod 4, so the MMA of input row i writes the three cyclically consecutive groups starting at
+// (i-2) mod 4 (two instructions when they wrap) while the fourth group - the output row completed by input
+// row i-1 - is being read out and re-armed with the bias.  Every staged row is read from shared memory by
+// 9 MMAs (bf16: 5) instead of 27 (15): 7-8 KB of operands per 128x96xK MMA instead of 5 KB per 128x32xK.
+//
+// The accumulators are never cleared or pre-loaded: the first MMA that contributes to an output row (kernel
+// row ky0, first K step) is issued on that row's group alone with accumulate = 0; everything else of an
+// interior input row is ONE instruction per K step over all four groups (N = 128) with a weight image
+// rotated by its start address, [ky2 | ky1 | ky0 | 0] landing on groups (i-2, i-1, i, i+1) mod 4 - the group
+// being read out only sees "+= 0".  Rows at the ends of a CTA's range use per-group N = 32 instructions.
+//
+// Warp roles (384 threads, 1 CTA/SM, each CTA owns a contiguous range of the global row sequence):
+//   warp 0      producer : cp.async.bulk of map rows into the slot ring           (empty[] -> full[])
+//   warps 1, 2  MMA issue: segment 0 / 1 (128 px each) of every staged row; each owns its accumulator tile
+//   warps 4-7   epilogue of segment 0, warps 8-11 of segment 1: tcgen05.ld of the finished group
+//               (lane = pixel), tcgen05.st of the bias, ReLU, rounding / packing or the fused 1x1 head +
+//               threshold, coalesced 16-byte stores
+#pragma once
+#include "ubd_tc.cuh"
+
+namespace tc4 {
+
+using tc::smem_u32; using tc::elect_one; using tc::mbar_init; using tc::mbar_arrive; using tc::mbar_expect_tx;
+using tc::mbar_wait; using tc::bulk_g2s; using tc::umma_commit; using tc::tc_fence_before; using tc::tc_fence_after;
+using tc::make_desc; using tc::round_tf32; using tc::pack_bf16x2; using tc::HeadArgs;
+
+// Bounded wait like tc::mbar_wait; on a stall every warp leaves (code << 24 | info) in gerr[1 + warp].
+__device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code, uint32_t info) {
+  const long long t0 = clock64();
+  bool ok = true;
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (*abort_flag || clock64() - t0 > 1500000000LL) {
+      atomicCAS(gerr, 0, code);
+      *abort_flag = 1;
+      gerr[1 + (threadIdx.x >> 5)] = (code << 24) | (int)(info & 0xFFFFFFu);
+      ok = false;
+      break;
+    }
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
+constexpr int PAD = UBD_MAP_PAD;
+constexpr int SEG = 128;
+constexpr int SW_MAX = 256;                               // strip = two segments
+constexpr int GROUP_BYTES = 32 * 16;                      // one group of a weight K-core: 32 oc rows x 16 B
+constexpr int KCORE_BYTES = 7 * GROUP_BYTES;              // groups hold kernel rows {ky0, -, ky2, ky1, ky0, -, ky2}
+constexpr int IMG_BYTES = 2 * KCORE_BYTES;                // 7168 per MMA: [2 K cores][7 groups][32 oc][16 B]
+constexpr int N_IMG_TF32 = 10, N_IMG_BF16 = 6;            // 9 (5) K steps + the first K step without ky0
+constexpr int W_BYTES_TF32 = N_IMG_TF32 * IMG_BYTES;      // 71680
+constexpr int W_BYTES_BF16 = N_IMG_BF16 * IMG_BYTES;      // 43008
+constexpr int WB_BYTES_TF32 = W_BYTES_TF32 + 128;         // + bias[32]
+constexpr int WB_BYTES_BF16 = W_BYTES_BF16 + 128;
+constexpr int SLOT_BYTES_TF32 = UBD_NG * (SW_MAX + 2 * PAD) * 16;      // 27648
+constexpr int SLOT_BYTES_BF16 = 3 * (SW_MAX + 2 * PAD) * 16;           // 13824
+constexpr int NS_TF32 = 5, NS_BF16 = 8;
+constexpr int THREADS = 384;
+constexpr int TMEM_COLS = 256;                            // per segment one tile of 4 groups x 32 columns
+
+template <bool BF16> struct Smem {
+  static constexpr int NS = BF16 ? NS_BF16 : NS_TF32;
+  static constexpr int SLOT = BF16 ? SLOT_BYTES_BF16 : SLOT_BYTES_TF32;
+  static constexpr int WB = BF16 ? WB_BYTES_BF16 : WB_BYTES_TF32;
+  uint8_t slots[NS * SLOT];
+  uint8_t wimg[WB];                                       // weight images, then bias[32]
+  float headw[UBD_NF * (1 + UBD_MAX_CLASSES) + 1 + UBD_MAX_CLASSES];
+  uint64_t full[NS], empty[NS], gfull[8], gempty[8], wbar;
+  uint32_t tmem_base;
+  int abort_flag;
+};
+
+// A contiguous run of output rows inside one (image, strip, y-phase).
+struct Piece { int n, x0, nw, c, j0, rows, R; };
+
+struct Walk {
+  long long t, t1;
+  int h, w, d, sw, n_strips, q, rem;
+  __device__ Walk(int n_imgs, int h_, int w_, int d_, int sw_, int cta, int n_cta) : h(h_), w(w_), d(d_), sw(sw_) {
+    n_strips = (w + sw - 1) / sw;
+    q = h / d; rem = h % d;
+    const long long total = (long long)n_imgs * n_strips * h;
+    t = total * cta / n_cta;
+    t1 = total * (cta + 1) / n_cta;
+  }
+  __device__ bool next(Piece& p) {
+    if (t >= t1) return false;
+    const long long is = t / h;
+    const int pos = (int)(t - is * h);
+    p.n = (int)(is / n_strips);
+    p.x0 = (int)(is % n_strips) * sw;
+    p.nw = min(sw, w - p.x0);
+    const int big = rem * (q + 1);
+    if (pos < big) { p.c = pos / (q + 1); p.j0 = pos % (q + 1); p.R = q + 1; }
+    else { const int p2 = pos - big; p.c = rem + p2 / q; p.j0 = p2 % q; p.R = q; }
+    p.rows = (int)min((long long)(p.R - p.j0), t1 - t);
+    t += p.rows;
+    return true;
+  }
+};
+
+__device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (bf16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// in / out: padded row-interleaved maps (pad = PAD) in 16-byte units (tf32: 6 planes of float4, bf16: 3
+// planes of 8 x bf16).  wb: this layer's weight images (tc3 layout) followed by bias[32].  sw: strip width.
+// out_mode 0: same format as the input (tf32 rna / bf16), 1: fp32 6-plane unrounded, 2: fused 1x1 head +
+// logit threshold (net.py:307-311, model_runner.py:124): the last map never reaches HBM.
+template <bool BF16>
+__global__ void __launch_bounds__(THREADS, 1)
+dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
+                   int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad, int* gerr, HeadArgs head, long long* trace) {
+  using S_t = Smem<BF16>;
+  constexpr int NS = S_t::NS;
+  constexpr int NGI = BF16 ? 3 : UBD_NG;
+  constexpr uint32_t WBB = S_t::WB;
+  constexpr uint32_t WBYTES = BF16 ? W_BYTES_BF16 : W_BYTES_TF32;
+  constexpr int N_STEP = BF16 ? 5 : 9;                      // K steps per input row; image N_STEP = step 0 without ky0
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  S_t& S = *reinterpret_cast<S_t*>(smem_raw);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  volatile int* abort_flag = &S.abort_flag;
+  // optional event trace of CTA 0 (tuning): trace[role][event][4] cycle stamps
+  const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
+  int tr_n = 0;
+#define TC4_TRACE(role, slot) do { if (tr && tr_n < 1024) trace[((role) * 1024 + tr_n) * 4 + (slot)] = clock64(); } while (0)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 2); }
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&S.gfull[i]), 1); mbar_init(smem_u32(&S.gempty[i]), 4); }
+    mbar_init(smem_u32(&S.wbar), 1);
+    S.abort_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+  const bool epi = warp >= 4;
+  const int quad = warp & 3;
+  const int seg = epi ? (warp - 4) >> 2 : (warp == 2 ? 1 : 0);       // segment column this warp works on
+  float bias[UBD_NF];
+  if (epi) {
+#pragma unroll
+    for (int c = 0; c < UBD_NF; ++c) bias[c] = __ldg(reinterpret_cast<const float*>(wb + WBYTES) + c);
+    if (out_mode == 2) {
+      const int et = (int)threadIdx.x - 128;                 // 0..255 over the epilogue warps
+      for (int i = et; i < UBD_NF * head.n_out; i += 256) S.headw[i] = head.hk[i];
+      for (int i = et; i < head.n_out; i += 256) S.headw[UBD_NF * head.n_out + i] = head.hb[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t slots0 = smem_u32(S.slots);
+  const int wp = w + 2 * PAD;
+  const int wpo = w + 2 * out_pad;
+  const uint32_t plane_bytes = (uint32_t)(sw + 2 * PAD) * 16;
+  const uint32_t slot_bytes = (uint32_t)NGI * plane_bytes;
+  const bool one_copy = (w == sw);
+  Walk walk(n_imgs, h, w, d, sw, (int)blockIdx.x, (int)gridDim.x);
+  Piece pc;
+  uint64_t* gfull = S.gfull + seg * 4;
+  uint64_t* gempty = S.gempty + seg * 4;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&S.wbar), WBB);
+      bulk_g2s(smem_u32(S.wimg), wb, WBB, smem_u32(&S.wbar));
+    }
+    uint32_t lseq = 0;
+    bool ok = true;
+    while (ok && walk.next(pc)) {
+      const uint32_t copy_bytes = (uint32_t)(pc.nw + 2 * PAD) * 16;
+      for (int i = 0; i < pc.rows + 2 && ok; ++i) {
+        const int jj = pc.j0 - 1 + i;
+        if (jj < 0 || jj >= pc.R) continue;                 // zero row above / below the image: no MMAs at all
+        const uint32_t slot = lseq % NS;
+        TC4_TRACE(0, 0);
+        ok = mbar_wait3(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 21, lseq);
+        if (!ok) break;
+        TC4_TRACE(0, 1);
+        const uint32_t bar = smem_u32(&S.full[slot]);
+        const uint32_t dst = slots0 + slot * S_t::SLOT;
+        const int y = pc.c + jj * d;
+        const uint4* src = in + (((size_t)pc.n * h + y) * NGI) * wp + pc.x0;
+        if (elect_one()) {
+          if (one_copy) {
+            mbar_expect_tx(bar, slot_bytes);
+            bulk_g2s(dst, src, slot_bytes, bar);
+          } else {
+            mbar_expect_tx(bar, (uint32_t)NGI * copy_bytes);
+            for (int g = 0; g < NGI; ++g) bulk_g2s(dst + g * plane_bytes, src + (size_t)g * wp, copy_bytes, bar);
+          }
+        }
+        __syncwarp();
+        TC4_TRACE(0, 2);
+        ++tr_n;
+        ++lseq;
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers (segment 0 / 1)
+    bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 22);
+    // weight images: K-major, LBO = K-core stride, SBO = 128 B; the run [ky2 | ky1 | ky0] starts at image group 2
+    const uint32_t b_lo0 = ((smem_u32(S.wimg) >> 4) & 0x3FFFu) | ((uint32_t)(KCORE_BYTES >> 4) << 16);
+    const uint32_t plane_units = plane_bytes >> 4;
+    const uint32_t a_lbo = (plane_units & 0x3FFFu) << 16;
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+    const uint32_t idesc0 = BF16 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24))
+                                 : ((1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24));
+    const uint32_t tmem_t = tmem_base + (uint32_t)seg * 128u;
+    uint32_t lseq = 0, par_e = 0;
+    while (ok && walk.next(pc)) {
+      const bool active = seg * SEG < pc.nw;                 // a narrow strip has no second segment
+      for (int i = 0; i < pc.rows + 2 && ok; ++i) {
+        if (warp == 1) TC4_TRACE(1, 0);
+        if (active && i < pc.rows) {
+          // output row i gets its first contribution now: its column group must have been drained and re-armed
+          const uint32_t bit = (uint32_t)(i & 3);
+          ok = mbar_wait3(smem_u32(&gempty[bit]), ((par_e >> bit) & 1u) ^ 1u, abort_flag, gerr, 23, (uint32_t)i);
+          par_e ^= 1u << bit;
+          if (!ok) break;
+          tc_fence_after();
+        }
+        if (warp == 1) TC4_TRACE(1, 1);
+        const int jj = pc.j0 - 1 + i;
+        const bool valid = jj >= 0 && jj < pc.R;
+        uint32_t slot = 0;
+        if (valid) {
+          slot = lseq % NS;
+          ok = mbar_wait3(smem_u32(&S.full[slot]), (lseq / NS) & 1, abort_flag, gerr, 24, (uint32_t)i);
+          if (!ok) break;
+          ++lseq;
+          tc_fence_after();
+        }
+        if (warp == 1) TC4_TRACE(1, 2);
+        // kernel rows t = 0, 1, 2 <-> (ky2, ky1, ky0) <-> output rows (i-2, i-1, i) <-> image groups (2, 3, 4) <->
+        // column groups (i-2, i-1, i) mod 4.  The first valid input row of an output row overwrites its group.
+        const uint32_t a_row = ((((slots0 + slot * S_t::SLOT) >> 4) & 0x3FFFu) | a_lbo) + PAD + (uint32_t)(seg * SEG);
+        const bool interior = i >= 2 && i < pc.rows;        // all three output rows exist (and were started earlier)
+        auto a_desc = [&](int m) -> uint64_t {                // A operand (pixels) of K step m
+          if constexpr (!BF16) {
+            const int dx = m / 3, kp = m % 3;
+            return make_desc(a_row + (uint32_t)((dx - 1) * d) + (uint32_t)kp * 2u * plane_units, DESC_HI);
+          } else {
+            const uint32_t a2 = (a_row & ~(0x3FFFu << 16)) + 2u * plane_units;
+            if (m < 3) return make_desc(a_row + (uint32_t)((m - 1) * d), DESC_HI);             // planes 0 + 1 of tap dx = m
+            if (m == 3) return make_desc((a2 + (uint32_t)(-d)) | ((uint32_t)d << 16), DESC_HI);  // plane 2 of dx = -1, 0 (LBO = d px)
+            return make_desc(a2 + (uint32_t)d, DESC_HI);                                         // plane 2 of dx = +1 (LBO = 0)
+          }
+        };
+        if (elect_one()) {
+          if (valid && active) {
+            if (interior) {
+              // image groups s..s+3 -> column groups 0..3 with ky2 on group (i-2) mod 4
+              const uint32_t b_rot = b_lo0 + (uint32_t)((4 - (i & 3)) & 3) * (GROUP_BYTES >> 4);
+              umma(BF16, tmem_t + (uint32_t)(i & 3) * 32u, a_desc(0), make_desc(b_lo0, DESC_HI), idesc0 | ((32u >> 3) << 17), 0u);
+              umma(BF16, tmem_t, a_desc(0), make_desc(b_rot + (uint32_t)N_STEP * (IMG_BYTES >> 4), DESC_HI), idesc0 | ((128u >> 3) << 17), 1u);
+#pragma unroll
+              for (int m = 1; m < N_STEP; ++m)
+                umma(BF16, tmem_t, a_desc(m), make_desc(b_rot + (uint32_t)m * (IMG_BYTES >> 4), DESC_HI), idesc0 | ((128u >> 3) << 17), 1u);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+                const int o = i - 2 + t;
+                if (o >= 0 && o < pc.rows) {
+                  const int first = (pc.j0 == 0 && o == 0) ? 1 : o;      // first input row of output o that exists
+                  const uint32_t tmem_d = tmem_t + (uint32_t)(o & 3) * 32u;
+                  const uint32_t b_g = b_lo0 + (uint32_t)(2 + t) * (GROUP_BYTES >> 4);
+#pragma unroll
+                  for (int m = 0; m < N_STEP; ++m)
+                    umma(BF16, tmem_d, a_desc(m), make_desc(b_g + (uint32_t)m * (IMG_BYTES >> 4), DESC_HI), idesc0 | ((32u >> 3) << 17),
+                         (m == 0 && i == first) ? 0u : 1u);
+                }
+              }
+            }
+          }
+          if (valid) {
+            if (active) umma_commit(smem_u32(&S.empty[slot])); else mbar_arrive(smem_u32(&S.empty[slot]));
+          }
+          if (active && i >= 2) umma_commit(smem_u32(&gfull[(i - 2) & 3]));
+        }
+        __syncwarp();
+        if (warp == 1) { TC4_TRACE(1, 3); ++tr_n; }
+      }
+    }
+  } else if (epi) {
+    // ------------------------------------------------------------------ epilogue (lane = pixel, 24 columns = channels)
+    const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)seg * 128u;
+    bool ok = true;
+    uint32_t par_f = 0;
+    while (ok && walk.next(pc)) {
+      if (seg * SEG >= pc.nw) continue;
+      for (int o = 0; o < pc.rows && ok; ++o) {
+        const uint32_t G = (uint32_t)(o & 3);
+        if (warp == 4) TC4_TRACE(2, 0);
+        ok = mbar_wait3(smem_u32(&gfull[G]), (par_f >> G) & 1u, abort_flag, gerr, 25, (uint32_t)o);
+        par_f ^= 1u << G;
+        if (!ok) break;
+        tc_fence_after();
+        if (warp == 4) TC4_TRACE(2, 1);
+        const uint32_t taddr = tq + G * 32u;
+        uint32_t v[24];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
+                     : "r"(taddr + 16));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&gempty[G]));
+        if (warp == 4) TC4_TRACE(2, 2);
+        const int y = pc.c + (pc.j0 + o) * d;
+        const int xs = seg * SEG + quad * 32 + lane;           // pixel inside the strip
+        if (xs < pc.nw) {
+          const int x = pc.x0 + xs;
+          float a[UBD_NF];
+#pragma unroll
+          for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
+          if (out_mode == 2) {
+            const size_t p = ((size_t)pc.n * h + y) * w + x;
+            const float* hw = S.headw;
+            float* lo = head.logits ? head.logits + p * head.n_out : nullptr;
+            for (int oc = 0; oc < head.n_out; ++oc) {
+              float acc = hw[UBD_NF * head.n_out + oc];
+#pragma unroll
+              for (int c = 0; c < UBD_NF; ++c) acc = fmaf(a[c], hw[c * head.n_out + oc], acc);
+              if (lo) lo[oc] = acc;
+              if (oc == 0 && head.mask) head.mask[p] = acc > head.thr ? 1 : 0;
+            }
+          } else if (BF16 && out_mode == 0) {
+            uint4* o_px = out + (((size_t)pc.n * h + y) * 3) * wpo + out_pad + x;
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+              o_px[(size_t)g * wpo] = make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
+                                                pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7]));
+          } else {
+            uint4* o_px = out + (((size_t)pc.n * h + y) * UBD_NG) * wpo + out_pad + x;
+            const bool rnd = !BF16 && out_mode == 0;
+#pragma unroll
+            for (int g = 0; g < UBD_NG; ++g) {
+              float4 q = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+              if (rnd) { q.x = round_tf32(q.x); q.y = round_tf32(q.y); q.z = round_tf32(q.z); q.w = round_tf32(q.w); }
+              o_px[(size_t)g * wpo] = *reinterpret_cast<uint4*>(&q);
+            }
+          }
+        }
+        if (warp == 4) { TC4_TRACE(2, 3); ++tr_n; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// Weight images of one layer from its Keras HWIO kernel (3,3,24,24) in the flat parameter buffer.
+// tf32: image m = dx*3 + kp (K step); [2 K cores][7 groups][32 oc rows][4 ic], group gi holds kernel row
+// {ky0, -, ky2, ky1}[gi & 3]; values rounded to tf32 (rna).  Image 9 = image 0 without ky0.  Then bias[32].
+__global__ void build_img_tf32_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
+                                      const int64_t* __restrict__ boff, uint8_t* __restrict__ dst_all) {
+  const int layer = blockIdx.x;
+  const float* K = params + koff[layer];
+  const float* B = params + boff[layer];
+  float* dst = reinterpret_cast<float*>(dst_all + (size_t)layer * WB_BYTES_TF32);
+  constexpr int PER_IMG = IMG_BYTES / 4, PER_CORE = KCORE_BYTES / 4;
+  for (int i = threadIdx.x; i < W_BYTES_TF32 / 4; i += blockDim.x) {
+    const int mi = i / PER_IMG, rem = i % PER_IMG;
+    const int m = mi == 9 ? 0 : mi;
+    const int kcore = rem / PER_CORE, r2 = rem % PER_CORE;
+    const int gi = r2 / 128, oc = (r2 % 128) / 4, col = r2 % 4;
+    const int blk = gi & 3;
+    int ky = blk == 0 ? 0 : (blk == 2 ? 2 : (blk == 3 ? 1 : -1));
+    if (mi == 9 && ky == 0) ky = -1;
+    const int dx = m / 3, kp = m % 3;
+    const int ic = kp * 8 + kcore * 4 + col;
+    dst[i] = (ky >= 0 && oc < UBD_NF) ? tc::round_tf32(K[((ky * 3 + dx) * UBD_NF + ic) * UBD_NF + oc]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[W_BYTES_TF32 / 4 + i] = i < UBD_NF ? B[i] : 0.f;
+}
+
+// bf16: images 0..2 = tap dx, ic 0..15; image 3 = K core 0: tap dx=-1, K core 1: tap dx=0, ic 16..23;
+// image 4 = K core 0: tap dx=+1, ic 16..23, K core 1 zero; image 5 = image 0 without ky0.
+__global__ void build_img_bf16_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
+                                      const int64_t* __restrict__ boff, uint8_t* __restrict__ dst_all) {
+  const int layer = blockIdx.x;
+  const float* K = params + koff[layer];
+  const float* B = params + boff[layer];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(dst_all + (size_t)layer * WB_BYTES_BF16);
+  constexpr int PER_IMG = IMG_BYTES / 2, PER_CORE = KCORE_BYTES / 2;
+  for (int i = threadIdx.x; i < W_BYTES_BF16 / 2; i += blockDim.x) {
+    const int mi = i / PER_IMG, rem = i % PER_IMG;
+    const int m = mi == 5 ? 0 : mi;
+    const int kcore = rem / PER_CORE, r2 = rem % PER_CORE;
+    const int gi = r2 / 256, oc = (r2 % 256) / 8, col = r2 % 8;
+    const int blk = gi & 3;
+    int ky = blk == 0 ? 0 : (blk == 2 ? 2 : (blk == 3 ? 1 : -1));
+    if (mi == 5 && ky == 0) ky = -1;
+    int dx = -1, ic = 0;
+    if (m < 3) { dx = m; ic = kcore * 8 + col; }
+    else if (m == 3) { dx = kcore; ic = 16 + col; }
+    else if (kcore == 0) { dx = 2; ic = 16 + col; }
+    const float v = (ky >= 0 && dx >= 0 && oc < UBD_NF) ? K[((ky * 3 + dx) * UBD_NF + ic) * UBD_NF + oc] : 0.f;
+    dst[i] = __float2bfloat16_rn(v);
+  }
+  float* bias = reinterpret_cast<float*>(dst_all + (size_t)layer * WB_BYTES_BF16 + W_BYTES_BF16);
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) bias[i] = i < UBD_NF ? B[i] : 0.f;
+}
+
+}  // namespace tc4
+
+static constexpr size_t kTc4Tf32 = (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_TF32;
+static constexpr size_t kTc4Bf16 = (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_BF16;
+
+static void tc4_setup_attributes() {
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<false>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
+}
+
+// Weight images, rebuilt whenever the parameters change (tc_prepare owns the error flag and the offsets table).
+static int tc4_prepare(ubd_handle h) {
+  int rc = tc_prepare(h);
+  if (rc) return rc;
+  if (!h->tc4_weights.p) {
+    UBD_CUDA(cudaMalloc(&h->tc4_weights.p, kTc4Tf32 + kTc4Bf16));
+    h->tc4_weights.cap = kTc4Tf32 + kTc4Bf16;
+    h->tc4_weights_dirty = true;
+  }
+  if (h->tc4_weights_dirty) {
+    const int64_t* d_offs = reinterpret_cast<const int64_t*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES + 64);
+    tc4::build_img_tf32_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p);
+    tc4::build_img_bf16_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p + kTc4Tf32);
+    h->launches += 2;
+    UBD_CUDA(cudaGetLastError());
+    h->tc4_weights_dirty = false;
+  }
+  return UBD_OK;
+}
+
+static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
+                              int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr) {
+  if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
+  int rc = tc4_prepare(h);
+  if (rc) return rc;
+  const bool bf16 = h->precision == UBD_BF16;
+  const uint8_t* base = (const uint8_t*)h->tc4_weights.p;
+  const uint8_t* wb = bf16 ? base + kTc4Tf32 + (size_t)layer * tc4::WB_BYTES_BF16 : base + (size_t)layer * tc4::WB_BYTES_TF32;
+  const int sw = ww <= tc4::SW_MAX ? ww : tc4::SW_MAX;
+  const int n_strips = (ww + sw - 1) / sw;
+  const long long rows = (long long)n * n_strips * hh;
+  const int grid = (int)std::min<long long>(rows, h->n_sm);
+  tc::HeadArgs ha{};
+  if (head) ha = *head;
+  if (bf16)
+    tc4::dilconv_col_kernel<true><<<grid, tc4::THREADS, sizeof(tc4::Smem<true>), h->stream>>>(
+        (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p);
+  else
+    tc4::dilconv_col_kernel<false><<<grid, tc4::THREADS, sizeof(tc4::Smem<false>), h->stream>>>(
+        (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p);
+  ++h->launches;
+  UBD_CUDA(cudaGetLastError());
+  return UBD_OK;
+}
