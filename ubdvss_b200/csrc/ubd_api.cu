@@ -197,7 +197,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
   else if (!strcmp(name, "tc_trace")) {
-    if (value) { ENSURE(h->tc_trace, 4 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
+    if (value) { ENSURE(h->tc_trace, 8 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
     else if (h->tc_trace.p) { cudaFree(h->tc_trace.p); h->tc_trace.p = nullptr; h->tc_trace.cap = 0; }
   }
   else if (!strcmp(name, "precision")) { if (value < UBD_FP32 || value > UBD_BF16) UBD_FAIL(UBD_ERR_ARG, "bad precision"); h->precision = (int)value; }
@@ -756,7 +756,7 @@ extern "C" int ubd_debug_read_trace(ubd_handle h, long long* out, int n_values) 
   if (!h || !out || !h->tc_trace.p) return UBD_ERR_ARG;
   UBD_CUDA(cudaSetDevice(h->device));
   UBD_CUDA(cudaStreamSynchronize(h->stream));
-  UBD_CUDA(cudaMemcpy(out, h->tc_trace.p, std::min<size_t>((size_t)n_values * 8, 4 * 1024 * 4 * 8), cudaMemcpyDeviceToHost));
+  UBD_CUDA(cudaMemcpy(out, h->tc_trace.p, std::min<size_t>((size_t)n_values * 8, 8 * 1024 * 4 * 8), cudaMemcpyDeviceToHost));
   UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap));
   return UBD_OK;
 }

@@ -8,10 +8,9 @@
 //
 // An input row r of a y-phase (rows c, c+d, c+2d, ...) contributes to the output rows r-1, r, r+1 through
 // the kernel rows ky = 2, 1, 0.  A segment's accumulator tile has four 32-column groups; output row o owns
-// group o mod 4, so the MMA of input row i writes the three cyclically consecutive groups starting at
-// (i-2) mod 4 (two instructions when they wrap) while the fourth group - the output row completed by input
-// row i-1 - is being read out and re-armed with the bias.  Every staged row is read from shared memory by
-// 9 MMAs (bf16: 5) instead of 27 (15): 7-8 KB of operands per 128x96xK MMA instead of 5 KB per 128x32xK.
+// group o mod 4, so input row i writes the groups (i-2, i-1, i) mod 4 while the fourth group - the output
+// row completed by input row i-1 - is being read out.  Every staged row is read from shared memory by 10
+// MMAs (bf16: 6) instead of 27 (15): 8 KB of operands per 128x128xK MMA instead of 5 KB per 128x32xK.
 //
 // The accumulators are never cleared or pre-loaded: the first MMA that contributes to an output row (kernel
 // row ky0, first K step) is issued on that row's group alone with accumulate = 0; everything else of an
@@ -23,8 +22,10 @@
 //   warp 0      producer : cp.async.bulk of map rows into the slot ring           (empty[] -> full[])
 //   warps 1, 2  MMA issue: segment 0 / 1 (128 px each) of every staged row; each owns its accumulator tile
 //   warps 4-7   epilogue of segment 0, warps 8-11 of segment 1: tcgen05.ld of the finished group
-//               (lane = pixel), tcgen05.st of the bias, ReLU, rounding / packing or the fused 1x1 head +
-//               threshold, coalesced 16-byte stores
+//               (lane = pixel), bias + ReLU, rounding / packing or the fused 1x1 head + threshold,
+//               coalesced 16-byte stores
+//   warps 12-20 (L1SRC variant, the stem's L2 layer as a dense conv): compute layer L1 (separable s2 1->24,
+//               FP32, exact) of every staged row straight into the slot ring instead of the TMA producer
 #pragma once
 #include "ubd_tc.cuh"
 
@@ -57,6 +58,10 @@ __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volati
   return __all_sync(0xffffffffu, ok);
 }
 
+// rna to the tf32 grid for finite, non-negative values (everything after a ReLU): add half an ulp of tf32, clear
+// the low 13 bits.  Two integer instructions; cvt.rna.tf32.f32 is emulated with four on sm_100a.
+__device__ __forceinline__ float rna_pos(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
 constexpr int PAD = UBD_MAP_PAD;
 constexpr int SEG = 128;
 constexpr int SW_MAX = 256;                               // strip = two segments
@@ -72,6 +77,8 @@ constexpr int SLOT_BYTES_TF32 = UBD_NG * (SW_MAX + 2 * PAD) * 16;      // 27648
 constexpr int SLOT_BYTES_BF16 = 3 * (SW_MAX + 2 * PAD) * 16;           // 13824
 constexpr int NS_TF32 = 5, NS_BF16 = 8;
 constexpr int THREADS = 384;
+constexpr int L1_THREADS = 288;                           // 9 L1-producer warps: one thread per staged pixel (sw + 2 = 258 are used)
+constexpr int THREADS_L1 = THREADS + L1_THREADS;
 constexpr int TMEM_COLS = 256;                            // per segment one tile of 4 groups x 32 columns
 
 template <bool BF16> struct Smem {
@@ -84,6 +91,8 @@ template <bool BF16> struct Smem {
   uint64_t full[NS], empty[NS], gfull[8], gempty[8], wbar;
   uint32_t tmem_base;
   int abort_flag;
+  float lut[256];                // L1-producer variant: uint8 -> preprocessed float
+  float l1w[9 + UBD_NF + UBD_NF]; // dw1[9], pw1[24], b1[24] (grey input)
 };
 
 // A contiguous run of output rows inside one (image, strip, y-phase).
@@ -131,13 +140,16 @@ __device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t adesc,
 }
 
 // in / out: padded row-interleaved maps (pad = PAD) in 16-byte units (tf32: 6 planes of float4, bf16: 3
-// planes of 8 x bf16).  wb: this layer's weight images (tc3 layout) followed by bias[32].  sw: strip width.
+// planes of 8 x bf16).  wb: this layer's weight images followed by bias[32].  sw: strip width.
 // out_mode 0: same format as the input (tf32 rna / bf16), 1: fp32 6-plane unrounded, 2: fused 1x1 head +
 // logit threshold (net.py:307-311, model_runner.py:124): the last map never reaches HBM.
-template <bool BF16>
-__global__ void __launch_bounds__(THREADS, 1)
+// out_mode 3: parity-split output [n][y][x & 1][plane][PAD + (x >> 1)] (input of the stride-2 layer).
+// L1SRC: `in` is the uint8 grey image, h / w the half-resolution map size, d = 1 (see tc::L1Args).
+template <bool BF16, bool L1SRC>
+__global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
 dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
-                   int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad, int* gerr, HeadArgs head, long long* trace) {
+                   int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad, int* gerr, HeadArgs head, long long* trace,
+                   tc::L1Args l1) {
   using S_t = Smem<BF16>;
   constexpr int NS = S_t::NS;
   constexpr int NGI = BF16 ? 3 : UBD_NG;
@@ -152,7 +164,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
   // optional event trace of CTA 0 (tuning): trace[role][event][4] cycle stamps
   const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
   int tr_n = 0;
-#define TC4_TRACE(role, slot) do { if (tr && tr_n < 1024) trace[((role) * 1024 + tr_n) * 4 + (slot)] = clock64(); } while (0)
+#define TC4_TRACE(role, slot) do { if (tr && tr_n < 1024) trace[(((L1SRC ? 4 : 0) + (role)) * 1024 + tr_n) * 4 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 2); }
@@ -169,7 +181,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
-  const bool epi = warp >= 4;
+  const bool epi = warp >= 4 && warp < 12;
   const int quad = warp & 3;
   const int seg = epi ? (warp - 4) >> 2 : (warp == 2 ? 1 : 0);       // segment column this warp works on
   float bias[UBD_NF];
@@ -204,7 +216,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
       bulk_g2s(smem_u32(S.wimg), wb, WBB, smem_u32(&S.wbar));
     }
     uint32_t lseq = 0;
-    bool ok = true;
+    bool ok = !L1SRC;                                      // L1SRC: the rows come from the L1 warps below
     while (ok && walk.next(pc)) {
       const uint32_t copy_bytes = (uint32_t)(pc.nw + 2 * PAD) * 16;
       for (int i = 0; i < pc.rows + 2 && ok; ++i) {
@@ -367,6 +379,22 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
               if (lo) lo[oc] = acc;
               if (oc == 0 && head.mask) head.mask[p] = acc > head.thr ? 1 : 0;
             }
+          } else if (out_mode == 3) {
+            constexpr int NGO = BF16 ? 3 : UBD_NG;
+            const size_t wps = (size_t)(w / 2 + 2 * PAD);
+            uint4* o_px = out + ((((size_t)pc.n * h + y) * 2 + (x & 1)) * NGO) * wps + PAD + (x >> 1);
+            if constexpr (BF16) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g)
+                o_px[(size_t)g * wps] = make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
+                                                   pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7]));
+            } else {
+#pragma unroll
+              for (int g = 0; g < UBD_NG; ++g) {
+                float4 q = make_float4(rna_pos(a[4 * g]), rna_pos(a[4 * g + 1]), rna_pos(a[4 * g + 2]), rna_pos(a[4 * g + 3]));
+                o_px[(size_t)g * wps] = *reinterpret_cast<uint4*>(&q);
+              }
+            }
           } else if (BF16 && out_mode == 0) {
             uint4* o_px = out + (((size_t)pc.n * h + y) * 3) * wpo + out_pad + x;
 #pragma unroll
@@ -379,12 +407,122 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
 #pragma unroll
             for (int g = 0; g < UBD_NG; ++g) {
               float4 q = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
-              if (rnd) { q.x = round_tf32(q.x); q.y = round_tf32(q.y); q.z = round_tf32(q.z); q.w = round_tf32(q.w); }
+              if (rnd) { q.x = rna_pos(q.x); q.y = rna_pos(q.y); q.z = rna_pos(q.z); q.w = rna_pos(q.w); }
               o_px[(size_t)g * wpo] = *reinterpret_cast<uint4*>(&q);
             }
           }
         }
         if (warp == 4) { TC4_TRACE(2, 3); ++tr_n; }
+      }
+    }
+  }
+
+  if (L1SRC && warp >= 12) {
+    // ------------------------------------------------------------------ L1 producers (9 warps)
+    // One thread = one staged pixel j of every row (map column x0 - 1 + j; only x0-1 .. x0+nw can be read
+    // by the d = 1 taps).  The image bytes of the NEXT row are loaded before waiting for its slot, so the
+    // global latency overlaps the wait and the previous row's arithmetic.  One warp polls the slot's
+    // barrier and one thread publishes the row: the group synchronises with a named barrier instead of 288
+    // mbarrier arrivals per row.
+    const int t = (int)threadIdx.x - THREADS;
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
+    for (int i = t; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
+    for (int i = t; i < 9 + 2 * UBD_NF; i += L1_THREADS)
+      S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 9 + UBD_NF ? l1.pw1[i - 9] : l1.b1[i - 9 - UBD_NF]);
+    asm volatile("bar.sync 1, 288;" ::: "memory");         // the L1 warps only
+    float dwr[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dwr[i] = S.l1w[i];
+    uint32_t lseq = 0;
+    bool ok = true;
+    while (ok && walk.next(pc)) {
+      const int x = pc.x0 - 1 + t;                           // this thread's map column
+      const bool use = t < pc.nw + 2;
+      const bool okx = use && x >= 0 && x < w;
+      // image columns 2x - pad_l + {0,1,2}: validity mask and pointer of the first one
+      uint32_t cm = 0u;
+#pragma unroll
+      for (int tj = 0; tj < 3; ++tj) {
+        const int ix = 2 * x - l1.pad_l + tj;
+        if (okx && ix >= 0 && ix < l1.W) cm |= 1u << tj;
+      }
+      const uint8_t* pcol = img + ((size_t)pc.n * l1.H) * l1.W + (2 * x - l1.pad_l);
+      // the 9 image bytes of map pixel (yy, x), one register each (0 where the tap is outside the image):
+      // nothing consumes them before the next row's arithmetic, so the loads really stay in flight
+      auto load9 = [&](int yy, uint32_t& valid, uint32_t (&r)[9]) {
+        valid = 0u;
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti) {
+          const int iy = 2 * yy - l1.pad_t + ti;
+          const bool rv = cm != 0u && iy >= 0 && iy < l1.H;
+          const uint8_t* p = pcol + (size_t)iy * l1.W;
+#pragma unroll
+          for (int tj = 0; tj < 3; ++tj) {
+            r[ti * 3 + tj] = 0u;
+            if (rv && (cm & (1u << tj))) r[ti * 3 + tj] = __ldg(p + tj);
+          }
+          if (rv) valid |= cm << (3 * ti);
+        }
+      };
+      int i = pc.j0 == 0 ? 1 : 0;                             // input rows that exist: jj = j0 - 1 + i in [0, R)
+      const int i_end = min(pc.rows + 1, pc.R - pc.j0);
+      uint32_t valid = 0u, b[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) b[q] = 0u;
+      if (i <= i_end) load9(pc.c + (pc.j0 - 1 + i) * d, valid, b);
+      for (; i <= i_end && ok; ++i, ++lseq) {
+        const uint32_t slot = lseq % NS;
+        if (warp == 12) TC4_TRACE(3, 0);
+        uint32_t nvalid = 0u, nb[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) nb[q] = 0u;
+        if (i + 1 <= i_end) load9(pc.c + (pc.j0 + i) * d, nvalid, nb);
+        if (warp == 12) mbar_wait3(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 26, lseq);
+        asm volatile("bar.sync 1, 288;" ::: "memory");
+        if (warp == 12) TC4_TRACE(3, 1);
+        ok = *abort_flag == 0;
+        if (ok && use) {
+          uint8_t* px = S.slots + (size_t)slot * S_t::SLOT + (size_t)(PAD - 1 + t) * 16;
+          if (okx) {
+            // depthwise 3x3 (stride 2) on the preprocessed bytes, pointwise 1 -> 24, bias, ReLU
+            float a = 0.f;
+            if (valid == 0x1FFu) {
+#pragma unroll
+              for (int q = 0; q < 9; ++q) a = fmaf(S.lut[b[q]], dwr[q], a);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 9; ++q)
+                if (valid & (1u << q)) a = fmaf(S.lut[b[q]], dwr[q], a);
+            }
+            float o[UBD_NF];
+#pragma unroll
+            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(fmaf(a, S.l1w[9 + c], S.l1w[9 + UBD_NF + c]), 0.f);
+            if constexpr (BF16) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g)
+                *reinterpret_cast<uint4*>(px + g * plane_bytes) =
+                    make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                               pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+            } else {
+#pragma unroll
+              for (int g = 0; g < UBD_NG; ++g)
+                *reinterpret_cast<float4*>(px + g * plane_bytes) =
+                    make_float4(rna_pos(o[4 * g]), rna_pos(o[4 * g + 1]), rna_pos(o[4 * g + 2]), rna_pos(o[4 * g + 3]));
+            }
+          } else {
+            // column outside the map: L2's zero padding
+#pragma unroll
+            for (int g = 0; g < (BF16 ? 3 : UBD_NG); ++g) *reinterpret_cast<uint4*>(px + g * plane_bytes) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        if (warp == 12) TC4_TRACE(3, 2);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 288;" ::: "memory");
+        if (ok && t == 0) mbar_arrive(smem_u32(&S.full[slot]));
+        if (warp == 12) { TC4_TRACE(3, 3); ++tr_n; }
+        valid = nvalid;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) b[q] = nb[q];
       }
     }
   }
@@ -452,12 +590,15 @@ __global__ void build_img_bf16_kernel(const float* __restrict__ params, const in
 
 }  // namespace tc4
 
-static constexpr size_t kTc4Tf32 = (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_TF32;
-static constexpr size_t kTc4Bf16 = (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_BF16;
+static constexpr int kTc4NumImg = UBD_NLAYERS_DIL + 1;          // + the stem's L2 as a merged dense 3x3 kernel
+static constexpr size_t kTc4Tf32 = (size_t)kTc4NumImg * tc4::WB_BYTES_TF32;
+static constexpr size_t kTc4Bf16 = (size_t)kTc4NumImg * tc4::WB_BYTES_BF16;
 
 static void tc4_setup_attributes() {
-  cudaFuncSetAttribute(tc4::dilconv_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<false>));
-  cudaFuncSetAttribute(tc4::dilconv_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<false>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<false>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
 }
 
 // Weight images, rebuilt whenever the parameters change (tc_prepare owns the error flag and the offsets table).
@@ -473,15 +614,23 @@ static int tc4_prepare(ubd_handle h) {
     const int64_t* d_offs = reinterpret_cast<const int64_t*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES + 64);
     tc4::build_img_tf32_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p);
     tc4::build_img_bf16_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p + kTc4Tf32);
-    h->launches += 2;
+    // image 6: the stem's L2 (separable 24->24) as one dense 3x3 kernel, merged by tc_prepare into h->l2dense
+    tc4::build_img_tf32_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
+                                                         (uint8_t*)h->tc4_weights.p + (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_TF32);
+    tc4::build_img_bf16_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
+                                                         (uint8_t*)h->tc4_weights.p + kTc4Tf32 + (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_BF16);
+    h->launches += 4;
     UBD_CUDA(cudaGetLastError());
     h->tc4_weights_dirty = false;
   }
   return UBD_OK;
 }
 
+// layer 0..5 = conv2d_1..6; layer 6 = the stem's L2 as a dense conv with `in` = uint8 grey image and L1
+// computed by the producer warps (l1 != nullptr).
 static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
-                              int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr) {
+                              int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr,
+                              const tc::L1Args* l1 = nullptr) {
   if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
   int rc = tc4_prepare(h);
   if (rc) return rc;
@@ -494,12 +643,14 @@ static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer
   const int grid = (int)std::min<long long>(rows, h->n_sm);
   tc::HeadArgs ha{};
   if (head) ha = *head;
-  if (bf16)
-    tc4::dilconv_col_kernel<true><<<grid, tc4::THREADS, sizeof(tc4::Smem<true>), h->stream>>>(
-        (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p);
-  else
-    tc4::dilconv_col_kernel<false><<<grid, tc4::THREADS, sizeof(tc4::Smem<false>), h->stream>>>(
-        (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p);
+  tc::L1Args la{};
+  if (l1) la = *l1;
+#define UBD_TC4_LAUNCH(BF, L1S, THR)                                                                                   \
+  tc4::dilconv_col_kernel<BF, L1S><<<grid, THR, sizeof(tc4::Smem<BF>), h->stream>>>(                                   \
+      (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p, la)
+  if (l1) { if (bf16) UBD_TC4_LAUNCH(true, true, tc4::THREADS_L1); else UBD_TC4_LAUNCH(false, true, tc4::THREADS_L1); }
+  else { if (bf16) UBD_TC4_LAUNCH(true, false, tc4::THREADS); else UBD_TC4_LAUNCH(false, false, tc4::THREADS); }
+#undef UBD_TC4_LAUNCH
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
