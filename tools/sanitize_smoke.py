@@ -15,6 +15,10 @@ lg = eng.forward(x[:1], _lib.PREPROC_MOBILENET)
 thr = float(np.quantile(lg[..., 0], 0.8))
 mask, logits, labels, comps, counts = eng.segment(x, thr, 10, _lib.PREPROC_MOBILENET, want_labels=True)
 print(prec, "segment ok", counts.tolist(), float(mask.mean()))
+# multi-row pieces per CTA, two strips per row in the stem (W/2 = 512 > 256)
+x2 = synth.synth_images(3, 320, 1024, seed=2)
+mask2, _, _, _, counts2 = eng.segment(x2, thr, 10, _lib.PREPROC_MOBILENET)
+print(prec, "segment (large) ok", counts2.tolist())
 xf = (x.astype(np.float32) - 127.5) / 127.5
 eng.forward(xf, _lib.PREPROC_NONE)
 m = synth.stress_masks(3, 40, 72, seed=2)

@@ -196,6 +196,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   }
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
+  else if (!strcmp(name, "stem_chunk")) h->opt_stem_chunk = (int)value;
   else if (!strcmp(name, "tc_trace")) {
     if (value) { ENSURE(h->tc_trace, 8 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
     else if (h->tc_trace.p) { cudaFree(h->tc_trace.p); h->tc_trace.p = nullptr; h->tc_trace.cap = 0; }
@@ -351,6 +352,7 @@ static int pick_chunk(ubd_handle h, int n, int H, int W) {
 static int pick_stem_chunk(ubd_handle h, int chunk, int H, int W) {
   const double per_img = (double)(H / 2) * (W / 2) * 96.0;        // one half-resolution map
   const int c = (int)(0.5e9 / per_img);
+  if (h->opt_stem_chunk > 0) return std::max(1, std::min(chunk, h->opt_stem_chunk));
   return std::max(1, std::min(chunk, std::min(std::max(c, 1), 16)));
 }
 
@@ -642,12 +644,23 @@ extern "C" int ubd_segment(ubd_handle h, const void* images, int in_dtype, int n
   // the mask / logits copies are queued before the component read-back so they overlap it
   rc = forward_device(h, h->d_images.p, in_dtype, n, H, W, preproc, (float*)h->d_logits.p, (uint8_t*)h->d_mask.p, logit_thr, images);
   if (rc) return rc;
-  if (mask_out) UBD_CUDA(cudaMemcpyAsync(mask_out, h->d_mask.p, q, cudaMemcpyDeviceToHost, h->stream));
-  if (logits_out) UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, q * h->spec.n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (mask_out || logits_out) {
+    // the result copies run on the copy stream so that they overlap the CC kernels
+    if (h->copy_events.empty()) {
+      cudaEvent_t ev;
+      UBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      h->copy_events.push_back(ev);
+    }
+    UBD_CUDA(cudaEventRecord(h->copy_events[0], h->stream));
+    UBD_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));
+    if (mask_out) UBD_CUDA(cudaMemcpyAsync(mask_out, h->d_mask.p, q, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (logits_out) UBD_CUDA(cudaMemcpyAsync(logits_out, h->d_logits.p, q * h->spec.n_out * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+  }
   const int n_cls = h->n_classes;
   rc = ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4,
                   min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
   if (rc) return rc;
+  if (mask_out || logits_out) UBD_CUDA(cudaStreamSynchronize(h->copy_stream));
   return h->precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
 }
 

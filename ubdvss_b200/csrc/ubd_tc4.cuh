@@ -62,6 +62,17 @@ __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volati
 // the low 13 bits.  Two integer instructions; cvt.rna.tf32.f32 is emulated with four on sm_100a.
 __device__ __forceinline__ float rna_pos(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
+// One non-blocking probe of a barrier phase (the fast path of the waits on the MMA warps' critical path).
+__device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+
 constexpr int PAD = UBD_MAP_PAD;
 constexpr int SEG = 128;
 constexpr int SW_MAX = 256;                               // strip = two segments
@@ -262,25 +273,27 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
       const bool active = seg * SEG < pc.nw;                 // a narrow strip has no second segment
       for (int i = 0; i < pc.rows + 2 && ok; ++i) {
         if (warp == 1) TC4_TRACE(1, 0);
-        if (active && i < pc.rows) {
-          // output row i gets its first contribution now: its column group must have been drained and re-armed
-          const uint32_t bit = (uint32_t)(i & 3);
-          ok = mbar_wait3(smem_u32(&gempty[bit]), ((par_e >> bit) & 1u) ^ 1u, abort_flag, gerr, 23, (uint32_t)i);
-          par_e ^= 1u << bit;
-          if (!ok) break;
-          tc_fence_after();
-        }
-        if (warp == 1) TC4_TRACE(1, 1);
+        // (a) output row i gets its first contribution now: its column group must have been read out;
+        // (b) the staged input row must have landed.  Both barriers are probed together first: in steady
+        // state they have completed long ago and the bounded (clocked) wait is never entered.
+        const bool need_g = active && i < pc.rows;
+        const uint32_t bit = (uint32_t)(i & 3);
         const int jj = pc.j0 - 1 + i;
         const bool valid = jj >= 0 && jj < pc.R;
-        uint32_t slot = 0;
-        if (valid) {
-          slot = lseq % NS;
-          ok = mbar_wait3(smem_u32(&S.full[slot]), (lseq / NS) & 1, abort_flag, gerr, 24, (uint32_t)i);
+        const uint32_t slot = lseq % NS;
+        const uint32_t g_par = ((par_e >> bit) & 1u) ^ 1u, f_par = (lseq / NS) & 1u;
+        uint32_t d1 = 1u, d2 = 1u;
+        if (need_g) d1 = mbar_probe(smem_u32(&gempty[bit]), g_par);
+        if (valid) d2 = mbar_probe(smem_u32(&S.full[slot]), f_par);
+        if (!__all_sync(0xffffffffu, (d1 & d2) != 0u)) {
+          if (need_g) ok = mbar_wait3(smem_u32(&gempty[bit]), g_par, abort_flag, gerr, 23, (uint32_t)i);
+          if (ok && valid) ok = mbar_wait3(smem_u32(&S.full[slot]), f_par, abort_flag, gerr, 24, (uint32_t)i);
           if (!ok) break;
-          ++lseq;
-          tc_fence_after();
         }
+        if (need_g) par_e ^= 1u << bit;
+        if (valid) ++lseq;
+        tc_fence_after();
+        if (warp == 1) TC4_TRACE(1, 1);
         if (warp == 1) TC4_TRACE(1, 2);
         // kernel rows t = 0, 1, 2 <-> (ky2, ky1, ky0) <-> output rows (i-2, i-1, i) <-> image groups (2, 3, 4) <->
         // column groups (i-2, i-1, i) mod 4.  The first valid input row of an output row overwrites its group.
