@@ -170,6 +170,60 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "postproc_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", {k: np.shape(v) for k, v in out.items()})
+    host_side_golden(ModelRunner, SegmapManager, utils)
+
+
+def host_side_golden(ModelRunner, SegmapManager, utils):
+    """The callers either side of the path: network input size rule
+    (segmap_manager.py:136-173), markup rescaling (model_runner.py:140-148, utils.py:67-69) and the CSV
+    writer (ResultSaver.save_markup_csv, model_runner.py:214-228), executed from the reference and stored as JSON."""
+    import json
+    import tempfile
+    from PIL import Image
+    from semantic_segmentation.data_markup import ObjectMarkup, ClassifiedObjectMarkup
+    from semantic_segmentation.model_runner import ResultSaver
+
+    class Cfg:
+        def __init__(self, mult, max_side):
+            self.m, self.s = mult, max_side
+
+        def get_side_multiple(self):
+            return self.m
+
+        def get_max_side(self):
+            return self.s
+
+    gold = {"sizes": [], "csv": [], "rescale": []}
+    for (w, h, mult, max_side, override) in [(3840, 2160, 64, 4096, None), (3840, 2160, 64, 512, None), (1000, 700, 64, 512, None),
+                                             (700, 1000, 64, 512, None), (640, 480, 64, 1024, None), (33, 20, 64, 512, None),
+                                             (95, 97, 64, 512, None), (96, 160, 64, 512, None), (1024, 1024, 64, 512, 1024),
+                                             (1500, 1100, 32, 512, 768), (800, 2400, 64, 1024, None), (224, 288, 64, 512, None)]:
+        img = Image.new("L", (w, h))
+        markup = [ObjectMarkup(np.array([10.0, 12.0, 50.0, 12.0, 50.0, 40.0, 10.0, 40.0]))]
+        rimg, rmark = SegmapManager._rescale_image_and_markup(img, markup, Cfg(mult, max_side), max_side=override)
+        gold["sizes"].append({"w": w, "h": h, "side_multiple": mult, "max_side": max_side, "override": override,
+                              "new_w": rimg.size[0], "new_h": rimg.size[1],
+                              "markup": [float(v) for v in rmark[0].bbox]})
+    objs = [ObjectMarkup(np.array([1, 2, 30, 4, 33, 44, 5, 40])), ClassifiedObjectMarkup(np.array([7, 8, 9, 10, 11, 12, 13, 14]), 3),
+            ObjectMarkup(np.array([100.9, 2.2, 300.5, 4.5, 330.1, 440.7, 50.0, 400.0]))]
+    for sel in ([0], [1], [0, 1, 2], []):
+        with tempfile.NamedTemporaryFile("r", suffix=".csv") as f:
+            ResultSaver.save_markup_csv(f.name, [objs[i] for i in sel])
+            gold["csv"].append({"select": sel, "text": open(f.name).read()})
+    gold["csv_objects"] = [{"bbox": [float(v) for v in o.bbox], "type": getattr(o, "object_type", None)} for o in objs]
+
+    class Meta:
+        def __init__(self, xs, ys):
+            self.xscale, self.yscale = xs, ys
+    found = [[objs[0], objs[1]], [objs[2]]]
+    metas = [Meta(1.5, 0.75), Meta(3840 / 3840, 2160 / 2176)]
+    res = ModelRunner.rescale(found, metas)
+    gold["rescale"] = {"scales": [[m.xscale, m.yscale] for m in metas],
+                       "boxes": [[[int(v) for v in o.bbox] for o in f] for f in res],
+                       "types": [[getattr(o, "object_type", None) for o in f] for f in res]}
+    path = os.path.join(ROOT, "tests", "golden", "host_golden.json")
+    json.dump(gold, open(path, "w"), indent=1)
+    print("wrote", path)
 
 
 if __name__ == "__main__":

@@ -52,3 +52,22 @@ class ModelRunner:
         assert len(found_objects) == len(meta_infos)
         return [[obj.create_same_markup(utils.rescale_bbox(obj.bbox, xscale=mi.xscale, yscale=mi.yscale))
                  for obj in objs] for objs, mi in zip(found_objects, meta_infos)]
+
+
+class ResultSaver:
+    """The on-disk result format of the reference (model_runner.py:154-228); only the CSV writer is part of
+    the path's boundary, visualisations are out of scope."""
+
+    @staticmethod
+    def save_markup_csv(filename, markups):
+        """One line per object: the eight corner coordinates truncated to int, an empty quoted field and,
+        for classified objects, the type id (model_runner.py:214-228)."""
+        from .data_markup import ClassifiedObjectMarkup
+        lines = []
+        for m in markups:
+            fields = [str(int(v)) for v in m.bbox] + ['""']
+            if isinstance(m, ClassifiedObjectMarkup):
+                fields.append(str(m.object_type))
+            lines.append(",".join(fields) + "\n")
+        with open(filename, "w") as fh:
+            fh.write("".join(lines))

@@ -1,4 +1,5 @@
-"""``SegmapManager.postprocess`` of the reference (segmap_manager.py:42-69) on the GPU."""
+"""``SegmapManager.postprocess`` of the reference (segmap_manager.py:42-69) on the GPU, and the caller-side
+size rule that decides what the network is fed (segmap_manager.py:136-173)."""
 from __future__ import annotations
 
 import numpy as np
@@ -37,3 +38,38 @@ class SegmapManager:
             cls = np.asarray(seg_map_class_logits, dtype=np.float32)[None]
         _, comps, _ = eng.postprocess(m[None], cls, min_area_x2=min_area_x2(min_area_threshold))
         return markups_from_components(comps, scale, seg_map_class_logits is not None)
+
+    @staticmethod
+    def network_input_size(w, h, net_config, max_side=None):
+        """(new_w, new_h) the reference resizes a w x h image to before the network
+        (segmap_manager.py:145-165): both sides become multiples of ``get_side_multiple()`` (nearest
+        multiple, Python's round-half-to-even, at least one); an image whose longer side exceeds
+        ``max_side`` (default ``get_max_side()``) gets that side set to ``max_side`` itself and the other
+        one scaled in proportion.  3840x2160 with multiple 64 -> 3840x2176 (config C)."""
+        mult = net_config.get_side_multiple()
+        limit = net_config.get_max_side() if max_side is None else max_side
+
+        def snap(v):
+            return max(1, round(v / mult)) * mult
+        longer = max(w, h)
+        if longer <= limit:
+            return snap(w), snap(h)
+        shrink = limit / longer
+        return (limit, snap(h * shrink)) if w > h else (snap(w * shrink), limit)
+
+    @staticmethod
+    def _rescale_image_and_markup(image, markup, net_config, max_side=None):
+        """segmap_manager.py:136-173: PIL image (and its markup, if any) at the network's input size;
+        bicubic resampling as the reference; markup corners are scaled, not rounded."""
+        from PIL import Image
+        w, h = image.size
+        new_w, new_h = SegmapManager.network_input_size(w, h, net_config, max_side)
+        resized = image.resize(size=(new_w, new_h), resample=Image.BICUBIC)
+        if not markup:
+            return resized, markup
+        sx, sy = new_w / w, new_h / h
+        scaled = []
+        for m in markup:
+            pts = np.array(m.bbox, dtype=np.float64).reshape(-1, 2) * np.array([[sx, sy]])
+            scaled.append(m.create_same_markup(pts.reshape(-1)))
+        return resized, scaled
