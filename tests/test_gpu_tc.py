@@ -73,3 +73,15 @@ def test_bf16_layer_matches_oracle(eng, layer, shape):
     k, b = _round_bf16(w[9 + 2 * layer]), w[10 + 2 * layer]
     ref = np.maximum(onet._conv3x3_np(x.astype(np.float64), k.astype(np.float64), onet.DILATIONS[layer]) + b, 0)
     assert np.abs(got - ref).max() <= 2e-4, np.abs(got - ref).max()
+
+
+def test_tf32_operands_are_truncated(eng):
+    """kind::tf32 ignores the low 13 mantissa bits of its operands: garbage there must not change the
+    result.  (The stem's L1 producers rely on it: they round by adding half a tf32 ulp without masking.)"""
+    rng = np.random.default_rng(7)
+    x = onet.round_tf32(np.maximum(rng.normal(0, 1, size=(2, 32, 128, 24)), 0).astype(np.float32))
+    noisy = (x.view(np.uint32) | rng.integers(0, 1 << 13, size=x.shape, dtype=np.uint32)).view(np.float32)
+    for layer in (0, 3):
+        a = eng.debug_dilated_layer(x, layer, "tf32")
+        b = eng.debug_dilated_layer(noisy, layer, "tf32")
+        assert np.array_equal(a, b)

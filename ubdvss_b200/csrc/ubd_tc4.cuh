@@ -61,6 +61,9 @@ __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volati
 // rna to the tf32 grid for finite, non-negative values (everything after a ReLU): add half an ulp of tf32, clear
 // the low 13 bits.  Two integer instructions; cvt.rna.tf32.f32 is emulated with four on sm_100a.
 __device__ __forceinline__ float rna_pos(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+// The same for a value that is only ever read by a kind::tf32 MMA: the tensor core ignores the low 13 mantissa
+// bits (tests/test_gpu_tc.py::test_tf32_operands_are_truncated), so adding half an ulp is the whole rounding.
+__device__ __forceinline__ float rna_mma(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
 
 // One non-blocking probe of a barrier phase (the fast path of the waits on the MMA warps' critical path).
 __device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
@@ -520,7 +523,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g)
                 *reinterpret_cast<float4*>(px + g * plane_bytes) =
-                    make_float4(rna_pos(o[4 * g]), rna_pos(o[4 * g + 1]), rna_pos(o[4 * g + 2]), rna_pos(o[4 * g + 3]));
+                    make_float4(rna_mma(o[4 * g]), rna_mma(o[4 * g + 1]), rna_mma(o[4 * g + 2]), rna_mma(o[4 * g + 3]));
             }
           } else {
             // column outside the map: L2's zero padding
