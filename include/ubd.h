@@ -79,7 +79,12 @@ int ubd_device_count(void);                         /* 0 when no CUDA device is 
  * bias; conv (3,3,24,24) HWIO, bias; head (1,1,24,1+C), bias).  n_elems[i] is checked. */
 int ubd_set_weights(ubd_handle h, const float* const* arrays, const int64_t* n_elems, int n_arrays);
 int ubd_get_weights(ubd_handle h, float* const* arrays, const int64_t* n_elems, int n_arrays);
-int ubd_set_option(ubd_handle h, const char* name, int64_t value);  /* "chunk", "max_comps", "max_points" */
+/* Tuning / diagnostic switches: "chunk" (images per sweep of the dilated layers, 0 = auto), "stem_chunk"
+ * (images per stem launch, 0 = auto), "max_comps" (component slots per image), "max_points" (hull
+ * candidate capacity), "precision" (UBD_FP32/TF32/BF16), "profile" (CUDA-event stage timers, see
+ * ubd_get_stat), "dense_l2" (0: depthwise stem on the FP32 pipes), "tc_variant" (0: first-generation
+ * tensor-core kernel for the dilated layers and the stem's L2), "tc_trace" (in-kernel cycle trace). */
+int ubd_set_option(ubd_handle h, const char* name, int64_t value);
 
 /* ---- inference ------------------------------------------------------------------------------ */
 

