@@ -262,11 +262,25 @@ ccl_slots_kernel(const int* __restrict__ labels, int* __restrict__ slot_of, Comp
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i0 = 0; i0 < h * w; i0 += blockDim.x) {
-    const int i = i0 + threadIdx.x;
-    const bool root = i < h * w && lab[i] == i;
-    const unsigned bits = __ballot_sync(0xffffffffu, root);
-    if (lane == 0) warp_cnt[wid] = __popc(bits);
+  const int hw = h * w;
+  const bool vec = (hw & 3) == 0;                            // rows of 4 labels are 16-byte aligned
+  // a thread ranks 4 consecutive pixels per round: 16 rounds of 3 barriers for a 256x256 map
+  for (int i0 = 0; i0 < hw; i0 += (int)blockDim.x * 4) {
+    const int ib = i0 + (int)threadIdx.x * 4;
+    int l4[4] = {-1, -1, -1, -1};
+    if (vec) {
+      if (ib < hw) { const int4 q = *reinterpret_cast<const int4*>(lab + ib); l4[0] = q.x; l4[1] = q.y; l4[2] = q.z; l4[3] = q.w; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (ib + k < hw) l4[k] = lab[ib + k];
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt += (l4[k] == ib + k) ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_cnt[wid] = incl;
     __syncthreads();
     if (wid == 0) {
       const int own = lane < nwarps ? warp_cnt[lane] : 0;
@@ -277,14 +291,19 @@ ccl_slots_kernel(const int* __restrict__ labels, int* __restrict__ slot_of, Comp
       if (lane == 31) chunk_total = v;
     }
     __syncthreads();
-    if (root) {
-      const int slot = base + warp_off[wid] + __popc(bits & ((1u << lane) - 1u));
-      so[i] = slot;
-      if (slot < max_comps) {
-        CompRec r; r.label = i; r.xmin = w; r.ymin = h; r.xmax = -1; r.ymax = -1;
-        r.n_pixels = 0; r.n_filled = 0; r.q3 = 0; r.q4 = 0;
-        cr[slot] = r;
-        for (int c = 0; c < n_cls; ++c) cls_sums[((size_t)n * max_comps + slot) * n_cls + c] = 0ull;
+    int slot = base + warp_off[wid] + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (l4[k] == ib + k) {
+        const int i = ib + k;
+        so[i] = slot;
+        if (slot < max_comps) {
+          CompRec r; r.label = i; r.xmin = w; r.ymin = h; r.xmax = -1; r.ymax = -1;
+          r.n_pixels = 0; r.n_filled = 0; r.q3 = 0; r.q4 = 0;
+          cr[slot] = r;
+          for (int c = 0; c < n_cls; ++c) cls_sums[((size_t)n * max_comps + slot) * n_cls + c] = 0ull;
+        }
+        ++slot;
       }
     }
     __syncthreads();
