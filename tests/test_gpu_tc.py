@@ -85,3 +85,20 @@ def test_tf32_operands_are_truncated(eng):
         a = eng.debug_dilated_layer(x, layer, "tf32")
         b = eng.debug_dilated_layer(noisy, layer, "tf32")
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_first_generation_kernel_still_matches(eng, precision):
+    """Option tc_variant 0 (ubd_tc.cuh, one output row per accumulator) and the default column-rotating
+    kernel compute the same layer: same operands, only the fp32 accumulation order differs."""
+    rng = np.random.default_rng(11)
+    x = np.maximum(rng.normal(0, 1, size=(3, 40, 272, 24)), 0).astype(np.float32)
+    x = onet.round_tf32(x) if precision == "tf32" else _round_bf16(x)
+    for layer in (1, 4):
+        new = eng.debug_dilated_layer(x, layer, precision)
+        eng.set_option("tc_variant", 0)
+        try:
+            old = eng.debug_dilated_layer(x, layer, precision)
+        finally:
+            eng.set_option("tc_variant", 1)
+        assert np.abs(new - old).max() <= 2e-4

@@ -335,7 +335,7 @@ static int launch_head(ubd_handle h, const float4* in, float* logits, uint8_t* m
 static int launch_dil_tc(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d, int out_mode,
                          const tc::HeadArgs* head = nullptr) {
   if (h->opt_tc_variant) return tc4_launch_dilconv(h, in, out, layer, n, hh, ww, d, out_mode, UBD_MAP_PAD, head);
-  return tc_launch_dilconv(h, in, out, layer, n, hh, ww, d, out_mode, UBD_MAP_PAD, nullptr, head);
+  return tc_launch_dilconv(h, in, out, layer, n, hh, ww, d, out_mode, UBD_MAP_PAD, head);
 }
 
 // Images per sweep of the dilated layers / head ("chunk") and per stem launch ("stem chunk").

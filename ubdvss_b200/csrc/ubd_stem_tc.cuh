@@ -505,10 +505,9 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
       h->act2_tag = tag;
     }
     tc::L1Args la{mob ? h->d_lut : nullptr, h->d_params + h->spec.off[0], h->d_params + h->spec.off[1], h->d_params + h->spec.off[2], H, W, p2, p2};
-    rc = h->opt_tc_variant ? tc4_launch_dilconv(h, d_img, act2, UBD_NLAYERS_DIL, n, H2, W2, 1, /*out_mode=*/3, UBD_MAP_PAD, nullptr, &la)
-                           : tc_launch_dilconv(h, d_img, act2, UBD_NLAYERS_DIL, n, H2, W2, 1, /*out_mode=*/3, /*out_pad=*/UBD_MAP_PAD, &la);
+    rc = tc4_launch_dilconv(h, d_img, act2, UBD_NLAYERS_DIL, n, H2, W2, 1, /*out_mode=*/3, UBD_MAP_PAD, nullptr, &la);
     if (rc) return rc;
-    return tc_launch_dilconv(h, act2, act3, UBD_NLAYERS_DIL + 1, n, H2 / 2, W2 / 2, 1, /*out_mode=*/0, UBD_MAP_PAD, nullptr, nullptr,
+    return tc_launch_dilconv(h, act2, act3, UBD_NLAYERS_DIL + 1, n, H2 / 2, W2 / 2, 1, /*out_mode=*/0, UBD_MAP_PAD, nullptr,
                              /*s2=*/p2 ? 1 : 2);
   } else if (h->spec.cin == 1) {
     if (in_dtype == UBD_U8) rc = stem12_launch<1, uint8_t>(h, (const uint8_t*)d_img, act2, mob ? h->d_lut : nullptr, 0.f, 0.f, n, H, W, p2);

@@ -1,4 +1,7 @@
-// tcgen05 implicit-GEMM path for the dilated 3x3 24->24 layers (net.py:298-304), sm_100a only.
+// First-generation tcgen05 implicit-GEMM kernel (one output row segment per accumulator), sm_100a only.
+// It runs the stem's L3 (separable 24->24, stride 2, as a dense stride-2 conv, s2 != 0) and - behind option
+// "tc_variant" 0 - the dilated 3x3 24->24 layers (net.py:298-304), whose default path is ubd_tc4.cuh.  This
+// header also owns the shared tcgen05 / mbarrier helpers, the error flag and the merged stem kernels.
 //
 // GEMM view of one output row segment:  D[128 px, 32 oc] += A[128 px, K] * B[K, 32 oc],
 //   K = 9 taps x 24 channels; kind::tf32 consumes K = 8 per instruction -> 27 MMAs per segment.
@@ -69,12 +72,8 @@ struct Smem {
   uint32_t tmem_base;
   int abort_flag;
   float headw[UBD_NF * (1 + UBD_MAX_CLASSES) + 1 + UBD_MAX_CLASSES];   // out_mode 2: head kernel [24][n_out], bias
-  float lut[256];                // L1-producer variant: uint8 -> preprocessed float
-  float l1w[9 + UBD_NF + UBD_NF]; // dw1[9], pw1[24], b1[24] (grey input)
 };
 constexpr size_t SMEM_BYTES = sizeof(Smem) + 128;
-constexpr int L1_THREADS = 288;               // 9 warps: one thread per staged map pixel (sw + 2 = 258 are used)
-constexpr int THREADS_L1 = THREADS + L1_THREADS;    // + manual 128 B alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -191,20 +190,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // sw: strip width (128 or 256).  out_mode: 0 = same format as the input, tf32 output rounded (rna);
 // 1 = fp32 6-plane output without rounding (last layer, feeds the fp32 head).
 //
-// L1SRC variant (the stem's L2 layer as a dense conv, ubd_stem_tc.cuh): `in` is the uint8 grey IMAGE;
-// four extra warps compute layer L1 (separable s2 1->24, FP32, exact) for every staged row directly
-// into the slot ring (generic-proxy stores + fence.proxy.async + 128 mbarrier arrivals), so the L1 map
-// never exists in HBM.  h, w are then the half-resolution map size, d = 1.
 // out_mode 2: the 1x1 head (net.py:307-311) and the logit threshold (model_runner.py:124) run in the
 // epilogue: the thread that owns a pixel holds its 24 channels, so the last map never reaches HBM.
 struct HeadArgs { const float* hk; const float* hb; int n_out; float thr; float* logits; uint8_t* mask; };
+// Arguments of the L1-producer variant of the column-rotating kernel (ubd_tc4.cuh): grey uint8 image -> L1 rows.
 struct L1Args { const float* lut; const float* dw1; const float* pw1; const float* b1; int H, W, pad_t, pad_l; };
 
-template <bool BF16, bool L1SRC>
-__global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
+template <bool BF16>
+__global__ void __launch_bounds__(THREADS, 1)
 dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
                   const uint8_t* __restrict__ zeros, int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad,
-                  int* gerr, long long* trace, L1Args l1, HeadArgs head, int s2) {
+                  int* gerr, long long* trace, HeadArgs head, int s2) {
   // s2 != 0: stride-2 conv (the stem's L3 as a dense conv).  The input map (2h rows) is stored split by
   // column parity, [n][y][parity][plane][k + PAD] with E[k] = column 2k, O[k] = column 2k+1, so the tap
   // (ti,tj) of output pixel x reads row 2y - pad + ti of array (tj - pad) & 1 at offset floor((tj - pad)/2):
@@ -225,7 +221,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
 #define TC_TRACE(role, slot, val) do { if (tr && tr_n < 1024) trace[((role) * 1024 + tr_n) * 4 + (slot)] = (val); } while (0)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), L1SRC ? L1_THREADS : 1); mbar_init(smem_u32(&S.empty[i]), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&S.tfull[i]), 1); mbar_init(smem_u32(&S.tempty[i]), 4); }
     mbar_init(smem_u32(&S.wbar), 1);
     S.abort_flag = 0;
@@ -254,7 +250,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
       bulk_g2s(smem_u32(S.wimg), wb, WBB, smem_u32(&S.wbar));
     }
     uint32_t lseq = 0;
-    bool ok = !L1SRC;                                      // L1SRC: the rows come from the L1 warps below
+    bool ok = true;
     for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
       Item it;
       if (!sched.get(idx, it)) continue;
@@ -384,92 +380,6 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
         }
       }
       lbase += s2 ? 2 * it.rows + 1 : it.rows + 2;
-    }
-  } else if (L1SRC && warp >= 7) {
-    // ------------------------------------------------------------------ L1 producers (9 warps)
-    // One thread = one map pixel of the staged row (only x in [x0-1, x0+sw] can be read by the d = 1
-    // taps).  The 9 image bytes of the NEXT row are loaded before waiting for its slot, so the global
-    // latency overlaps the wait and the previous row's arithmetic.
-    const int t = (int)threadIdx.x - THREADS;              // 0..287
-    const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
-    for (int i = t; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
-    for (int i = t; i < 9 + 2 * UBD_NF; i += L1_THREADS) S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 9 + UBD_NF ? l1.pw1[i - 9] : l1.b1[i - 9 - UBD_NF]);
-    asm volatile("bar.sync 1, 288;" ::: "memory");         // the L1 warps only
-    float dwr[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) dwr[i] = S.l1w[i];
-    // bytes of the 3x3 image patch of map pixel (yy, x); 0 where the tap is outside the image
-    auto load9 = [&](const uint8_t* irow, int yy, int x, uint32_t& valid, uint32_t b[3]) {
-      valid = 0u;
-#pragma unroll
-      for (int ti = 0; ti < 3; ++ti) {
-        b[ti] = 0u;
-        const int iy = 2 * yy - l1.pad_t + ti;
-#pragma unroll
-        for (int tj = 0; tj < 3; ++tj) {
-          const int ix = 2 * x - l1.pad_l + tj;
-          if (iy >= 0 && iy < l1.H && ix >= 0 && ix < l1.W) {
-            b[ti] |= (uint32_t)__ldg(irow + (size_t)iy * l1.W + ix) << (8 * tj);
-            valid |= 1u << (ti * 3 + tj);
-          }
-        }
-      }
-    };
-    auto l1_store = [&](uint8_t* sl, int i, bool inside, uint32_t valid, const uint32_t b[3]) {
-      float o[UBD_NF];
-      if (inside) {
-        float a = 0.f;
-#pragma unroll
-        for (int ti = 0; ti < 3; ++ti)
-#pragma unroll
-          for (int tj = 0; tj < 3; ++tj)
-            if (valid & (1u << (ti * 3 + tj))) a = fmaf(S.lut[(b[ti] >> (8 * tj)) & 255u], dwr[ti * 3 + tj], a);
-#pragma unroll
-        for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(fmaf(a, S.l1w[9 + c], S.l1w[9 + UBD_NF + c]), 0.f);
-      } else {
-#pragma unroll
-        for (int c = 0; c < UBD_NF; ++c) o[c] = 0.f;
-      }
-      uint8_t* px = sl + (size_t)(PAD - 1 + i) * 16;
-      if constexpr (BF16) {
-#pragma unroll
-        for (int g = 0; g < NG_BF16; ++g)
-          *reinterpret_cast<uint4*>(px + g * plane_bytes) =
-              make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                         pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
-      } else {
-#pragma unroll
-        for (int g = 0; g < UBD_NG; ++g)
-          *reinterpret_cast<float4*>(px + g * plane_bytes) =
-              make_float4(round_tf32(o[4 * g]), round_tf32(o[4 * g + 1]), round_tf32(o[4 * g + 2]), round_tf32(o[4 * g + 3]));
-      }
-    };
-    uint32_t lseq = 0;
-    bool ok = true;
-    for (int idx = blockIdx.x; idx < sched.total && ok; idx += gridDim.x) {
-      Item it;
-      if (!sched.get(idx, it)) continue;
-      const uint8_t* irow = img + ((size_t)it.n * l1.H) * l1.W;
-      const int x = it.x0 - 1 + t;                           // this thread's map column
-      const bool x_ok = x >= 0 && x < w && t < sw + 2;
-      uint32_t valid = 0u, b[3] = {0u, 0u, 0u};
-      int q = it.q0 - 1;
-      if (x_ok && q >= 0 && q < h) load9(irow, q, x, valid, b);
-      for (; q <= it.q0 + it.rows && ok; ++q, ++lseq) {
-        const uint32_t slot = lseq % NS;
-        const bool row_ok = q >= 0 && q < h;                 // d = 1: phase row = map row
-        ok = mbar_wait(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 8);
-        if (!ok) break;
-        uint8_t* sl = S.slots + slot * slot_bytes;
-        // issue the next row's loads first, then do this row's arithmetic under their latency
-        const int qn = q + 1;
-        uint32_t nvalid = 0u, nb[3] = {0u, 0u, 0u};
-        if (qn <= it.q0 + it.rows && x_ok && qn >= 0 && qn < h) load9(irow, qn, x, nvalid, nb);
-        if (t < sw + 2) l1_store(sl, t, row_ok && x_ok, valid, b);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(smem_u32(&S.full[slot]));
-        valid = nvalid; b[0] = nb[0]; b[1] = nb[1]; b[2] = nb[2];
-      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
@@ -641,10 +551,8 @@ __global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const i
 }  // namespace tc
 
 static void tc_setup_attributes() {
-  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  cudaFuncSetAttribute(tc::dilconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
 }
 
 // tc_weights buffer: [6 x WB_BYTES tf32 images][6 x WB_BYTES_BF16 bf16 images][zero page][err flag][offsets]
@@ -706,11 +614,10 @@ static inline int* tc_err_flag(ubd_handle h) {
 }
 
 // in / out: padded maps in the precision's layout (tf32: 6 float4 planes, bf16: 3 planes of 8 bf16).
-// out_mode 1 writes fp32 6-plane output (last layer -> fp32 head).  layer 0..5 = conv2d_1..6; layer 6 =
-// the stem's L2 as a dense conv with `in` = uint8 grey image and L1 computed by the producer warps.
+// out_mode 1 writes fp32 6-plane output.  layer 0..5 = conv2d_1..6 (option "tc_variant" 0); layer 7 = the stem's
+// L3 as a merged dense stride-2 kernel (s2 = 1: FML padding, 2: none).
 static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
-                             int out_mode, int out_pad = UBD_MAP_PAD, const tc::L1Args* l1 = nullptr,
-                             const tc::HeadArgs* head = nullptr, int s2 = 0) {
+                             int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr, int s2 = 0) {
   if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
   int rc = tc_prepare(h);
   if (rc) return rc;
@@ -723,16 +630,14 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
   const int n_chunks = ((hh + d - 1) / d + tc::RQ - 1) / tc::RQ;
   const long long items = (long long)n * n_strips * d * n_chunks;
   const int grid = (int)std::min<long long>(items, h->n_sm);
-  tc::L1Args la{};
-  if (l1) la = *l1;
   tc::HeadArgs ha{};
   if (head) ha = *head;
-#define UBD_TC_LAUNCH(BF, L1S, THR)                                                                                     \
-  tc::dilconv_tc_kernel<BF, L1S><<<grid, THR, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw, \
-                                                                           out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, la, ha, s2)
-  if (l1) { if (bf16) UBD_TC_LAUNCH(true, true, tc::THREADS_L1); else UBD_TC_LAUNCH(false, true, tc::THREADS_L1); }
-  else { if (bf16) UBD_TC_LAUNCH(true, false, tc::THREADS); else UBD_TC_LAUNCH(false, false, tc::THREADS); }
-#undef UBD_TC_LAUNCH
+  if (bf16)
+    tc::dilconv_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw,
+                                                                                 out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, ha, s2);
+  else
+    tc::dilconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, h->stream>>>((const uint4*)in, (uint4*)out, wb, zeros, n, hh, ww, d, sw,
+                                                                                  out_mode, out_pad, tc_err_flag(h), (long long*)h->tc_trace.p, ha, s2);
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
