@@ -181,7 +181,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
 #define TC4_TRACE(role, slot) do { if (tr && tr_n < 1024) trace[(((L1SRC ? 4 : 0) + (role)) * 1024 + tr_n) * 4 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), 1); mbar_init(smem_u32(&S.empty[i]), 2); }
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), L1SRC ? L1_THREADS / 32 : 1); mbar_init(smem_u32(&S.empty[i]), 2); }
     for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&S.gfull[i]), 1); mbar_init(smem_u32(&S.gempty[i]), 4); }
     mbar_init(smem_u32(&S.wbar), 1);
     S.abort_flag = 0;
@@ -445,9 +445,9 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     // ------------------------------------------------------------------ L1 producers (9 warps)
     // One thread = one staged pixel j of every row (map column x0 - 1 + j; only x0-1 .. x0+nw can be read
     // by the d = 1 taps).  The image bytes of the NEXT row are loaded before waiting for its slot, so the
-    // global latency overlaps the wait and the previous row's arithmetic.  One warp polls the slot's
-    // barrier and one thread publishes the row: the group synchronises with a named barrier instead of 288
-    // mbarrier arrivals per row.
+    // global latency overlaps the wait and the previous row's arithmetic.  The nine warps run independently
+    // (each waits for the slot and publishes its 32 pixels with one arrival), so a slow warp does not hold
+    // the others back; they are only bounded by the slot ring.
     const int t = (int)threadIdx.x - THREADS;
     const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
     for (int i = t; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
@@ -501,10 +501,8 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
 #pragma unroll
         for (int q = 0; q < 9; ++q) nb[q] = 0u;
         if (i + 1 <= i_end) load9(pc.c + (pc.j0 + i) * d, nvalid, nb);
-        if (warp == 12) mbar_wait3(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 26, lseq);
-        asm volatile("bar.sync 1, 288;" ::: "memory");
+        ok = mbar_wait3(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 26, lseq);
         if (warp == 12) TC4_TRACE(3, 1);
-        ok = *abort_flag == 0;
         if (ok && use) {
           uint8_t* px = S.slots + (size_t)slot * S_t::SLOT + (size_t)(PAD - 1 + t) * 16;
           if (okx) {
@@ -541,8 +539,8 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         }
         if (warp == 12) TC4_TRACE(3, 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 288;" ::: "memory");
-        if (ok && t == 0) mbar_arrive(smem_u32(&S.full[slot]));
+        __syncwarp();
+        if (ok && lane == 0) mbar_arrive(smem_u32(&S.full[slot]));
         if (warp == 12) { TC4_TRACE(3, 3); ++tr_n; }
         valid = nvalid;
 #pragma unroll
