@@ -15,10 +15,11 @@ LIB = os.path.join(CSRC, "libubd.so")
 STAMP = os.path.join(CSRC, ".libubd.stamp")
 SOURCES = ["ubd_api.cu", "ubd_rect.cpp"]
 
+# UBD_TC_TRACE=1 in the environment compiles the in-kernel cycle trace in (tools/tc_trace.py, tools/stem_trace.py)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-]
+] + (["-DUBD_TC_TRACE=1"] if os.environ.get("UBD_TC_TRACE") == "1" else [])
 
 
 def _digest() -> str:

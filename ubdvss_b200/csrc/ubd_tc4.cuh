@@ -28,6 +28,9 @@
 //               FP32, exact) of every staged row straight into the slot ring instead of the TMA producer
 #pragma once
 #include "ubd_tc.cuh"
+#ifndef UBD_TC_TRACE
+#define UBD_TC_TRACE 0
+#endif
 
 namespace tc4 {
 
@@ -37,7 +40,7 @@ using tc::make_desc; using tc::round_tf32; using tc::pack_bf16x2; using tc::Head
 
 // Bounded wait like tc::mbar_wait; on a stall every warp leaves (code << 24 | info) in gerr[1 + warp].
 __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code, uint32_t info) {
-  const long long t0 = clock64();
+  uint32_t polls = 0;                                        // bounded by poll count: no clock reads on the fast path
   bool ok = true;
   while (true) {
     uint32_t done;
@@ -47,10 +50,10 @@ __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volati
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    if (*abort_flag || clock64() - t0 > 1500000000LL) {
+    if (*abort_flag || ++polls > 20000000u) {                // a failed try_wait takes >= ~50 cycles: ~1 s
       atomicCAS(gerr, 0, code);
       *abort_flag = 1;
-      gerr[1 + (threadIdx.x >> 5)] = (code << 24) | (int)(info & 0xFFFFFFu);
+      gerr[1 + ((threadIdx.x >> 5) & 15)] = (code << 24) | (int)(info & 0xFFFFFFu);
       ok = false;
       break;
     }
@@ -176,9 +179,17 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
   const int lane = threadIdx.x & 31;
   volatile int* abort_flag = &S.abort_flag;
   // optional event trace of CTA 0 (tuning): trace[role][event][4] cycle stamps
+  // (compiled in with -DUBD_TC_TRACE=1 only: the stamps cost clock reads and issue slots in every role)
+#if UBD_TC_TRACE
   const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
   int tr_n = 0;
 #define TC4_TRACE(role, slot) do { if (tr && tr_n < 1024) trace[(((L1SRC ? 4 : 0) + (role)) * 1024 + tr_n) * 4 + (slot)] = clock64(); } while (0)
+#define TC4_TRACE_NEXT() (++tr_n)
+#else
+  (void)trace;
+#define TC4_TRACE(role, slot) do { } while (0)
+#define TC4_TRACE_NEXT() do { } while (0)
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&S.full[i]), L1SRC ? L1_THREADS / 32 : 1); mbar_init(smem_u32(&S.empty[i]), 2); }
@@ -264,7 +275,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         }
         __syncwarp();
         TC4_TRACE(0, 2);
-        ++tr_n;
+        TC4_TRACE_NEXT();
         ++lseq;
       }
     }
@@ -353,7 +364,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
           if (active && i >= 2) umma_commit(smem_u32(&gfull[(i - 2) & 3]));
         }
         __syncwarp();
-        if (warp == 1) { TC4_TRACE(1, 3); ++tr_n; }
+        if (warp == 1) { TC4_TRACE(1, 3); TC4_TRACE_NEXT(); }
       }
     }
   } else if (epi) {
@@ -436,7 +447,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
             }
           }
         }
-        if (warp == 4) { TC4_TRACE(2, 3); ++tr_n; }
+        if (warp == 4) { TC4_TRACE(2, 3); TC4_TRACE_NEXT(); }
       }
     }
   }
@@ -471,19 +482,27 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         if (okx && ix >= 0 && ix < l1.W) cm |= 1u << tj;
       }
       const uint8_t* pcol = img + ((size_t)pc.n * l1.H) * l1.W + (2 * x - l1.pad_l);
+      const size_t W1 = (size_t)l1.W;
       // the 9 image bytes of map pixel (yy, x), one register each (0 where the tap is outside the image):
       // nothing consumes them before the next row's arithmetic, so the loads really stay in flight
       auto load9 = [&](int yy, uint32_t& valid, uint32_t (&r)[9]) {
+        const int iy0 = 2 * yy - l1.pad_t;
+        const uint8_t* p = pcol + (ptrdiff_t)iy0 * (ptrdiff_t)W1;
+        if (cm == 7u && iy0 >= 0 && iy0 + 2 < l1.H) {        // interior patch: nine plain loads
+          r[0] = __ldg(p); r[1] = __ldg(p + 1); r[2] = __ldg(p + 2);
+          r[3] = __ldg(p + W1); r[4] = __ldg(p + W1 + 1); r[5] = __ldg(p + W1 + 2);
+          r[6] = __ldg(p + 2 * W1); r[7] = __ldg(p + 2 * W1 + 1); r[8] = __ldg(p + 2 * W1 + 2);
+          valid = 0x1FFu;
+          return;
+        }
         valid = 0u;
 #pragma unroll
         for (int ti = 0; ti < 3; ++ti) {
-          const int iy = 2 * yy - l1.pad_t + ti;
-          const bool rv = cm != 0u && iy >= 0 && iy < l1.H;
-          const uint8_t* p = pcol + (size_t)iy * l1.W;
+          const bool rv = cm != 0u && iy0 + ti >= 0 && iy0 + ti < l1.H;
 #pragma unroll
           for (int tj = 0; tj < 3; ++tj) {
             r[ti * 3 + tj] = 0u;
-            if (rv && (cm & (1u << tj))) r[ti * 3 + tj] = __ldg(p + tj);
+            if (rv && (cm & (1u << tj))) r[ti * 3 + tj] = __ldg(p + ti * W1 + tj);
           }
           if (rv) valid |= cm << (3 * ti);
         }
@@ -541,7 +560,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (ok && lane == 0) mbar_arrive(smem_u32(&S.full[slot]));
-        if (warp == 12) { TC4_TRACE(3, 3); ++tr_n; }
+        if (warp == 12) { TC4_TRACE(3, 3); TC4_TRACE_NEXT(); }
         valid = nvalid;
 #pragma unroll
         for (int q = 0; q < 9; ++q) b[q] = nb[q];
