@@ -61,11 +61,10 @@ __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volati
   return __all_sync(0xffffffffu, ok);
 }
 
-// rna to the tf32 grid for finite, non-negative values (everything after a ReLU): add half an ulp of tf32, clear
-// the low 13 bits.  Two integer instructions; cvt.rna.tf32.f32 is emulated with four on sm_100a.
-__device__ __forceinline__ float rna_pos(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
-// The same for a value that is only ever read by a kind::tf32 MMA: the tensor core ignores the low 13 mantissa
-// bits (tests/test_gpu_tc.py::test_tf32_operands_are_truncated), so adding half an ulp is the whole rounding.
+// Rounding (rna) to the tf32 grid of a finite, non-negative value (everything after a ReLU) that is only ever
+// read by a kind::tf32 MMA: the tensor core ignores the low 13 mantissa bits
+// (tests/test_gpu_tc.py::test_tf32_operands_are_truncated), so adding half a tf32 ulp is the whole rounding -
+// one integer instruction where cvt.rna.tf32.f32 is emulated with four on sm_100a.
 __device__ __forceinline__ float rna_mma(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
 
 // One non-blocking probe of a barrier phase (the fast path of the waits on the MMA warps' critical path).
@@ -426,7 +425,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
             } else {
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g) {
-                float4 q = make_float4(rna_pos(a[4 * g]), rna_pos(a[4 * g + 1]), rna_pos(a[4 * g + 2]), rna_pos(a[4 * g + 3]));
+                float4 q = make_float4(rna_mma(a[4 * g]), rna_mma(a[4 * g + 1]), rna_mma(a[4 * g + 2]), rna_mma(a[4 * g + 3]));
                 o_px[(size_t)g * wps] = *reinterpret_cast<uint4*>(&q);
               }
             }
@@ -442,7 +441,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
 #pragma unroll
             for (int g = 0; g < UBD_NG; ++g) {
               float4 q = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
-              if (rnd) { q.x = rna_pos(q.x); q.y = rna_pos(q.y); q.z = rna_pos(q.z); q.w = rna_pos(q.w); }
+              if (rnd) { q.x = rna_mma(q.x); q.y = rna_mma(q.y); q.z = rna_mma(q.z); q.w = rna_mma(q.w); }
               o_px[(size_t)g * wpo] = *reinterpret_cast<uint4*>(&q);
             }
           }
@@ -468,7 +467,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     float dwr[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) dwr[i] = S.l1w[i];
-    uint32_t lseq = 0;
+    uint32_t lseq = 0, ring_slot = 0, ring_phase = 0;        // ring position = (lseq % NS, (lseq / NS) & 1)
     bool ok = true;
     while (ok && walk.next(pc)) {
       const int x = pc.x0 - 1 + t;                           // this thread's map column
@@ -514,13 +513,14 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
       for (int q = 0; q < 9; ++q) b[q] = 0u;
       if (i <= i_end) load9(pc.c + (pc.j0 - 1 + i) * d, valid, b);
       for (; i <= i_end && ok; ++i, ++lseq) {
-        const uint32_t slot = lseq % NS;
+        const uint32_t slot = ring_slot, ring_par = ring_phase ^ 1u;
+        if (++ring_slot == NS) { ring_slot = 0; ring_phase ^= 1u; }
         if (warp == 12) TC4_TRACE(3, 0);
         uint32_t nvalid = 0u, nb[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) nb[q] = 0u;
         if (i + 1 <= i_end) load9(pc.c + (pc.j0 + i) * d, nvalid, nb);
-        ok = mbar_wait3(smem_u32(&S.empty[slot]), ((lseq / NS) & 1) ^ 1, abort_flag, gerr, 26, lseq);
+        ok = mbar_wait3(smem_u32(&S.empty[slot]), ring_par, abort_flag, gerr, 26, lseq);
         if (warp == 12) TC4_TRACE(3, 1);
         if (ok && use) {
           uint8_t* px = S.slots + (size_t)slot * S_t::SLOT + (size_t)(PAD - 1 + t) * 16;
