@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Event trace of CTA 0 of the stem's L2 launch (L1-producer variant of the column-rotating kernel)."""
+"""Event trace of CTA 0 of the stem's L2 launch (L1-producer variant of the column-rotating kernel).
+Needs a trace-enabled build: UBD_TC_TRACE=1 python -m ubdvss_b200.build --force."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

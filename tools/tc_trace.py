@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Dump the event trace of CTA 0 of one tcgen05 dilated-conv launch (tuning aid)."""
+"""Dump the event trace of CTA 0 of one tcgen05 dilated-conv launch (tuning aid).
+Needs a trace-enabled build: UBD_TC_TRACE=1 python -m ubdvss_b200.build --force."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

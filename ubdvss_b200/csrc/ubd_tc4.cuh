@@ -31,6 +31,9 @@
 #ifndef UBD_TC_TRACE
 #define UBD_TC_TRACE 0
 #endif
+#ifndef UBD_L1_WARPS
+#define UBD_L1_WARPS 9
+#endif
 
 namespace tc4 {
 
@@ -93,7 +96,9 @@ constexpr int SLOT_BYTES_TF32 = UBD_NG * (SW_MAX + 2 * PAD) * 16;      // 27648
 constexpr int SLOT_BYTES_BF16 = 3 * (SW_MAX + 2 * PAD) * 16;           // 13824
 constexpr int NS_TF32 = 5, NS_BF16 = 8;
 constexpr int THREADS = 384;
-constexpr int L1_THREADS = 288;                           // 9 L1-producer warps: one thread per staged pixel (sw + 2 = 258 are used)
+constexpr int L1_WARPS = UBD_L1_WARPS;                    // L1-producer warps; each owns L1_PXW consecutive staged pixels
+constexpr int L1_PXW = (SW_MAX + 2 + L1_WARPS - 1) / L1_WARPS;   // (sw + 2 = 258 staged pixels per row)
+constexpr int L1_THREADS = 32 * L1_WARPS;
 constexpr int THREADS_L1 = THREADS + L1_THREADS;
 constexpr int TMEM_COLS = 256;                            // per segment one tile of 4 groups x 32 columns
 
@@ -458,12 +463,13 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     // global latency overlaps the wait and the previous row's arithmetic.  The nine warps run independently
     // (each waits for the slot and publishes its 32 pixels with one arrival), so a slow warp does not hold
     // the others back; they are only bounded by the slot ring.
-    const int t = (int)threadIdx.x - THREADS;
+    const int tl = (int)threadIdx.x - THREADS;              // 0 .. L1_THREADS-1 (table loads)
+    const int t = (warp - 12) * L1_PXW + lane;              // staged pixel of this thread
     const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
-    for (int i = t; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
-    for (int i = t; i < 9 + 2 * UBD_NF; i += L1_THREADS)
+    for (int i = tl; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
+    for (int i = tl; i < 9 + 2 * UBD_NF; i += L1_THREADS)
       S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 9 + UBD_NF ? l1.pw1[i - 9] : l1.b1[i - 9 - UBD_NF]);
-    asm volatile("bar.sync 1, 288;" ::: "memory");         // the L1 warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(L1_THREADS) : "memory");   // the L1 warps only
     float dwr[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) dwr[i] = S.l1w[i];
@@ -471,7 +477,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     bool ok = true;
     while (ok && walk.next(pc)) {
       const int x = pc.x0 - 1 + t;                           // this thread's map column
-      const bool use = t < pc.nw + 2;
+      const bool use = lane < L1_PXW && t < pc.nw + 2;
       const bool okx = use && x >= 0 && x < w;
       // image columns 2x - pad_l + {0,1,2}: validity mask and pointer of the first one
       uint32_t cm = 0u;
