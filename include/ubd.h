@@ -146,6 +146,11 @@ int ubd_grad_buffer(ubd_handle h, void** d_ptr, int64_t* n_floats);
 /* Keras-2 Adam (train.py:110): grads are multiplied by grad_scale first (1/world after a sum
  * all-reduce); step count is kept in the handle. */
 int ubd_adam_step(ubd_handle h, float lr, float beta_1, float beta_2, float epsilon, float grad_scale);
+
+/* Pixel statistics of the last ubd_train_step / ubd_loss batch for the training metrics the reference logs
+ * (keras_metrics.py:116-191): counts[6] = tp, tn, fp, fn of the detection channel (prediction: logit > 0,
+ * truth: y_true > 0), then correct / total class predictions over object pixels (arg-max class vs y_true - 1). */
+int ubd_metric_counts(ubd_handle h, int64_t* counts);
 int ubd_synchronize(ubd_handle h);
 /* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
  * instead of the handle's own, so that the caller's events bracket the work.  NULL restores it. */

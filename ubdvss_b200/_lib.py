@@ -58,6 +58,7 @@ SIGNATURES = {
     "ubd_get_grads": (_i, [_vp, _pp, _pi64, _i]),
     "ubd_grad_buffer": (_i, [_vp, _pp, _pi64]),
     "ubd_adam_step": (_i, [_vp, _f, _f, _f, _f, _f]),
+    "ubd_metric_counts": (_i, [_vp, _vp]),
     "ubd_debug_dilated_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),
     "ubd_debug_read_trace": (_i, [_vp, _vp, _i]),
     "ubd_synchronize": (_i, [_vp]),

@@ -53,16 +53,17 @@ struct ubd_handle_s {
   DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
   DevBuf tc4_weights;             // per-layer weight images of the column-rotating kernel (+ bias)
   // training workspaces
-  DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss;
+  DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss, d_metric;
   int64_t adam_t = 0;
   int train_n = 0, train_h = 0, train_w = 0;   // geometry the training maps were last zeroed for
   bool have_grads = false;
+  size_t loss_pixels = 0;         // pixels of the logits / targets of the last loss evaluation (ubd_metric_counts)
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
             &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
-            &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss};
+            &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
   }
 };
 

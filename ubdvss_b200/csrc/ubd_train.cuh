@@ -75,6 +75,32 @@ loss_pixel_kernel(const float* __restrict__ logits, const int* __restrict__ y_tr
   }
 }
 
+// Pixel statistics behind the training metrics (keras_metrics.py:116-191): confusion counts of the detection
+// channel (prediction = logit > 0, truth = y_true > 0) and, over the pixels of objects, how often the arg-max
+// class (first maximum, as tf.argmax) equals the label y_true - 1.  counts: tp, tn, fp, fn, cls_correct, cls_total.
+__global__ void __launch_bounds__(256)
+metric_counts_kernel(const float* __restrict__ logits, const int* __restrict__ y_true, int n_out, size_t P,
+                     unsigned long long* __restrict__ counts) {
+  unsigned c[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    const float* lg = logits + p * n_out;
+    const int yt = y_true[p];
+    const bool t = yt > 0, d = lg[0] > 0.f;
+    c[t ? (d ? 0 : 3) : (d ? 2 : 1)] += 1u;
+    if (n_out > 1 && t) {
+      int best = 1;
+      for (int k = 2; k < n_out; ++k) if (lg[k] > lg[best]) best = k;
+      c[4] += best == yt ? 1u : 0u;
+      c[5] += 1u;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const unsigned w = __reduce_add_sync(0xffffffffu, c[i]);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(counts + i, (unsigned long long)w);
+  }
+}
+
 __global__ void loss_reduce_kernel(const double* __restrict__ partials, int nblocks, size_t P, LossState* st) {
   if (threadIdx.x != 0) { if (threadIdx.x < 256) st->hist[threadIdx.x] = 0; return; }
   st->hist[0] = 0;

@@ -183,6 +183,12 @@ class Engine:
         check(self._h, self._lib.ubd_grad_buffer(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def metric_counts(self):
+        """(tp, tn, fp, fn, cls_correct, cls_total) of the last train_step / loss batch (keras_metrics.py:116-191)."""
+        c = np.zeros(6, np.int64)
+        check(self._h, self._lib.ubd_metric_counts(self._h, ptr(c)))
+        return c
+
     def adam_step(self, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, grad_scale=1.0):
         check(self._h, self._lib.ubd_adam_step(self._h, lr, beta_1, beta_2, epsilon, grad_scale))
 

@@ -46,3 +46,32 @@ def detection_and_classification_loss(y_true, y_pred):
 def get_loss(classification_mode=False):
     """losses.py:20-24."""
     return detection_and_classification_loss if classification_mode else detection_loss
+
+
+class _LossComponent:
+    """Metric token for one component of the loss (losses.py:139-208); value from the loss kernels' parts
+    ``[loss, positive, negative, hard_negative, classification, k]``."""
+
+    def __init__(self, name, fn, doc):
+        self.__name__ = name
+        self.__doc__ = doc
+        self._fn = fn
+
+    def __call__(self, counts, parts):
+        return float(self._fn(parts))
+
+
+_detection_part = _LossComponent(
+    "detection_loss", lambda p: L_POSITIVE_WEIGHT * p[1] + L_NEGATIVE_WEIGHT * p[2] + L_HARD_NEGATIVE_WEIGHT * p[3], "losses.py:33-44")
+pixel_positive_loss = _LossComponent("pixel_positive_loss", lambda p: p[1], "losses.py:139-149")
+pixel_negative_loss = _LossComponent("pixel_negative_loss", lambda p: p[2], "losses.py:153-167")
+pixel_hard_negative_loss = _LossComponent("pixel_hard_negative_loss", lambda p: p[3], "losses.py:170-191")
+classification_loss = _LossComponent("classification_loss", lambda p: p[4], "losses.py:65-83")
+
+
+def get_losses(classification_mode=False):
+    """losses.py:194-208: the loss components in the order the reference logs them."""
+    out = [_detection_part, pixel_positive_loss, pixel_negative_loss, pixel_hard_negative_loss]
+    if classification_mode:
+        out.append(classification_loss)
+    return out

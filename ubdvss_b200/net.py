@@ -264,8 +264,17 @@ class B200Model:
             raise ValueError("loss must come from ubdvss_b200.losses.get_loss (losses.py:20-24)")
         if self.n_classes and not self._classification_loss:
             raise ValueError("a model with a class head trains with detection_and_classification_loss (train.py:111)")
-        self.metrics_names = ["loss", "positive_loss", "negative_loss", "hard_negative_loss"] + \
-                             (["classification_loss"] if self._classification_loss else [])
+        # metrics: tokens from keras_metrics.get_all_metrics / losses.get_losses (train.py:112); without them the
+        # loss components are returned under their own names
+        self._metric_fns = list(metrics) if metrics else None
+        if self._metric_fns is not None:
+            for m in self._metric_fns:
+                if not (callable(m) and hasattr(m, "__name__") and hasattr(m, "_fn")):
+                    raise ValueError("metrics must come from ubdvss_b200.keras_metrics.get_all_metrics / losses.get_losses")
+            self.metrics_names = ["loss"] + [m.__name__ for m in self._metric_fns]
+        else:
+            self.metrics_names = ["loss", "positive_loss", "negative_loss", "hard_negative_loss"] + \
+                                 (["classification_loss"] if self._classification_loss else [])
 
     def set_distributed(self, enabled=True):
         """Data-parallel training: all-reduce the flat gradient buffer over torch.distributed (NCCL)
@@ -300,6 +309,13 @@ class B200Model:
         scale = self._allreduce_grads() if self._dist is not None else 1.0
         o = self._optimizer
         self._engine.adam_step(o.lr, o.beta_1, o.beta_2, o.epsilon, scale)
+        return self._batch_outputs(parts)
+
+    def _batch_outputs(self, parts):
+        """``[loss, *metrics]`` of the batch the engine has just evaluated."""
+        if getattr(self, "_metric_fns", None) is not None:
+            counts = self._engine.metric_counts()
+            return [float(parts[0])] + [m(counts, parts) for m in self._metric_fns]
         out = [float(parts[0]), float(parts[1]), float(parts[2]), float(parts[3])]
         if self._classification_loss:
             out.append(float(parts[4]))
@@ -308,10 +324,7 @@ class B200Model:
     def test_on_batch(self, x, y, sample_weight=None):
         logits = self.predict(x)
         parts, _ = self._engine.loss(logits, y)
-        out = [float(parts[0]), float(parts[1]), float(parts[2]), float(parts[3])]
-        if self._classification_loss:
-            out.append(float(parts[4]))
-        return out
+        return self._batch_outputs(parts)
 
     def fit_generator(self, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None,
                       validation_data=None, validation_steps=None, max_queue_size=10, workers=0,
