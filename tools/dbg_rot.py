@@ -1,4 +1,4 @@
-"""Bring-up helper for the row-rotating tcgen05 kernel: one layer, one shape, against the oracle."""
+"""Bring-up helper for the tcgen05 dilated-layer kernels: one layer, one shape, against the oracle."""
 import sys, time
 import numpy as np
 from oracle import net as onet
