@@ -221,9 +221,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    from oracle import net as onet, postproc as pp      # oracle: weights init + CPU baseline only
+    from ubdvss_b200 import synth as usynth
 
-    weights = onet.init_weights(0, seed=1234)
+    weights = usynth.synth_weights(0, seed=1234)               # random init of the architecture (no oracle on this arm)
     cfg = {"workload": f"configs[1]: batch-{args.batch} synthetic {args.size}x{args.size} grayscale inference per GPU, "
                        f"{args.precision}, threshold + CC boxes", "batch_per_gpu": args.batch, "image": [args.size, args.size, 1],
            "input_dtype": "uint8 (mobilenet_like preprocessing folded into L1)", "precision": args.precision,
@@ -234,6 +234,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        from oracle import net as onet                       # the reference arm IS the oracle port (TF/Keras absent)
         imgs = make_images(args.cpu_sample, args.size)
         xs = onet.preprocess(imgs[:1].astype(np.float64), "mobilenet_like").astype(np.float32)
         thr = float(np.quantile(onet.forward_torch(weights, xs)[..., 0], 0.9))

@@ -97,3 +97,20 @@ def synth_targets(n, h, w, n_classes=0, seed=0):
             cls = int(rng.integers(1, max(n_classes, 1) + 1))
             out[i, ..., 0][inside] = cls
     return out
+
+
+def synth_weights(n_classes=0, seed=1234, grey=True, bias_std=0.1):
+    """Random-init weights of the architecture (no checkpoints ship with the reference): Glorot-uniform
+    kernels as Keras initialises them (net.py:226) and N(0, bias_std) biases so that the bias paths are
+    exercised; the 23 arrays in ``get_weights()`` order."""
+    from .engine import weight_shapes
+    rng = np.random.default_rng(seed)
+    out = []
+    for shape in weight_shapes(grey, n_classes):
+        if len(shape) == 1:
+            out.append((rng.standard_normal(shape) * bias_std).astype(np.float32))
+        else:
+            kh, kw, cin, cout = shape
+            limit = np.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
+            out.append(rng.uniform(-limit, limit, size=shape).astype(np.float32))
+    return out
