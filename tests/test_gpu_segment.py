@@ -106,3 +106,28 @@ def test_rescale():
     found = [[ObjectMarkup(np.arange(8)), ClassifiedObjectMarkup(np.arange(8) + 1, 3)]]
     out = ModelRunner.rescale(found, [MI()])
     assert list(out[0][0].bbox) == [0, 0, 4, 1, 8, 2, 12, 3] and out[0][1].object_type == 3
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_chunking_does_not_change_results(precision):
+    """The batch is swept in chunks (dilated layers) and sub-chunks (stem); any split must give the same masks,
+    logits and components as one sweep: images are independent (model_runner.py:127-134)."""
+    from ubdvss_b200 import _lib
+    from ubdvss_b200.engine import Engine
+    w = onet.init_weights(0, seed=7)
+    x = synth.synth_images(11, 128, 320, seed=4)
+    outs = []
+    for chunk, stem_chunk in ((0, 0), (4, 3), (5, 1)):
+        eng = Engine(precision=precision)
+        eng.set_weights(w)
+        if chunk:
+            eng.set_option("chunk", chunk)
+            eng.set_option("stem_chunk", stem_chunk)
+        lg = eng.forward(x[:2], _lib.PREPROC_MOBILENET)
+        thr = float(np.quantile(lg[..., 0], 0.85))
+        outs.append((thr,) + tuple(eng.segment(x, outs[0][0] if outs else thr, 10, _lib.PREPROC_MOBILENET)))
+    mask0, logits0, _, comps0, counts0 = outs[0][1:]
+    for o in outs[1:]:
+        mask, logits, _, comps, counts = o[1:]
+        assert np.array_equal(mask, mask0) and np.array_equal(logits, logits0)
+        assert np.array_equal(counts, counts0) and np.array_equal(comps["box"], comps0["box"])
