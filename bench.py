@@ -418,7 +418,7 @@ def main():
                 "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum())}
         if not args.no_train:
             line["train_step"] = {"config": "configs[4]: forward + losses.py loss + backward + Adam, batch 32 of 512x512 per GPU, fp32"
-                                            + (", NCCL gradient all-reduce" if world > 1 else ""),
+                                            + (", gradient all-reduce over NCCL inside libubd (ubd_allreduce_grads)" if world > 1 else ""),
                                   "ms_per_step": train_ms_max, "images_per_sec": 32 * world / (train_ms_max / 1e3),
                                   "loss": train_loss}
         if world == 1 and not args.no_cpu_baseline:

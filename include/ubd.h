@@ -147,6 +147,15 @@ int ubd_grad_buffer(ubd_handle h, void** d_ptr, int64_t* n_floats);
  * all-reduce); step count is kept in the handle. */
 int ubd_adam_step(ubd_handle h, float lr, float beta_1, float beta_2, float epsilon, float grad_scale);
 
+/* Data-parallel training exchange (one process per GPU; the reference is single-GPU, train.py): rank 0 creates a
+ * 128-byte NCCL unique id and hands it to every rank out of band; each rank joins with ubd_comm_init; between
+ * ubd_train_step and ubd_adam_step(grad_scale = 1/world) ubd_allreduce_grads sums the flat gradient buffer over
+ * the ranks in place on the handle's stream.  NCCL is bound at run time (dlopen "libnccl.so.2"). */
+int ubd_comm_unique_id(void* id128);
+int ubd_comm_init(ubd_handle h, const void* id128, int rank, int world);
+int ubd_allreduce_grads(ubd_handle h);
+int ubd_comm_destroy(ubd_handle h);
+
 /* Pixel statistics of the last ubd_train_step / ubd_loss batch for the training metrics the reference logs
  * (keras_metrics.py:116-191): counts[6] = tp, tn, fp, fn of the detection channel (prediction: logit > 0,
  * truth: y_true > 0), then correct / total class predictions over object pixels (arg-max class vs y_true - 1). */

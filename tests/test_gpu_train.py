@@ -163,3 +163,23 @@ def test_full_size_config_e_step_is_finite_and_reproducible():
     parts, dl = eng.loss(logits, y)
     assert abs(parts[0] - p1[0]) <= 1e-5 * abs(p1[0])
     assert abs(g1[22][0] - dl.sum(dtype=np.float64)) <= 1e-4 * max(1.0, np.abs(dl).sum())
+
+
+def test_native_nccl_exchange_world_of_one():
+    """ubd_comm_unique_id / ubd_comm_init / ubd_allreduce_grads on a one-rank communicator: the sum over ranks is
+    the identity and the step that follows is the single-GPU step.  (Two or more ranks: tools/dist_train_check.py
+    under torchrun; the bench's train_step runs through this path for N > 1.)"""
+    from ubdvss_b200.engine import Engine
+    w = onet.init_weights(0, seed=3)
+    x = synth.synth_images(2, 64, 96, seed=2)
+    y = synth.synth_targets(2, 16, 24, 0, seed=2)
+    eng = _engine()
+    eng.set_weights(w)
+    eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    g0 = [g.copy() for g in eng.get_grads()]
+    eng.comm_init(Engine.comm_unique_id(), 0, 1)
+    eng.allreduce_grads()
+    g1 = eng.get_grads()
+    assert all(np.array_equal(a, b) for a, b in zip(g0, g1))
+    eng.adam_step()
+    assert any(not np.array_equal(a, b) for a, b in zip(w, eng.get_weights()))

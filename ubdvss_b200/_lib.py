@@ -59,6 +59,10 @@ SIGNATURES = {
     "ubd_grad_buffer": (_i, [_vp, _pp, _pi64]),
     "ubd_adam_step": (_i, [_vp, _f, _f, _f, _f, _f]),
     "ubd_metric_counts": (_i, [_vp, _vp]),
+    "ubd_comm_unique_id": (_i, [_vp]),
+    "ubd_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "ubd_allreduce_grads": (_i, [_vp]),
+    "ubd_comm_destroy": (_i, [_vp]),
     "ubd_debug_dilated_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),
     "ubd_debug_read_trace": (_i, [_vp, _vp, _i]),
     "ubd_synchronize": (_i, [_vp]),

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
 #include "ubd_ccl.cuh"
 #include "ubd_common.cuh"
 #include "ubd_fp32.cuh"
@@ -138,6 +139,7 @@ extern "C" int ubd_destroy(ubd_handle h) {
   if (!h) return UBD_ERR_ARG;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->nccl_comm) ubd_comm_destroy(h);
   for (DevBuf* b : h->all_bufs()) if (b->p) cudaFree(b->p);
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_lut) cudaFree(h->d_lut);

@@ -57,6 +57,8 @@ struct ubd_handle_s {
   int64_t adam_t = 0;
   int train_n = 0, train_h = 0, train_w = 0;   // geometry the training maps were last zeroed for
   bool have_grads = false;
+  void* nccl_comm = nullptr;      // ncclComm_t of the data-parallel group (ubd_comm_init)
+  int nccl_world = 0;
   size_t loss_pixels = 0;         // pixels of the logits / targets of the last loss evaluation (ubd_metric_counts)
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 

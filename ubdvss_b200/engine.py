@@ -183,6 +183,24 @@ class Engine:
         check(self._h, self._lib.ubd_grad_buffer(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    # ---------------------------------------------------------------- data-parallel exchange (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id; create on rank 0 and hand to every rank (any channel)."""
+        buf = np.zeros(128, np.uint8)
+        check(None, _lib.load().ubd_comm_unique_id(ptr(buf)))
+        return buf.tobytes()
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = np.frombuffer(unique_id, np.uint8).copy()
+        assert buf.size == 128
+        check(self._h, self._lib.ubd_comm_init(self._h, ptr(buf), int(rank), int(world)))
+        self.world = int(world)
+
+    def allreduce_grads(self):
+        """Sum of the flat gradient buffer over the ranks, in place, on the handle's stream."""
+        check(self._h, self._lib.ubd_allreduce_grads(self._h))
+
     def metric_counts(self):
         """(tp, tn, fp, fn, cls_correct, cls_total) of the last train_step / loss batch (keras_metrics.py:116-191)."""
         c = np.zeros(6, np.int64)

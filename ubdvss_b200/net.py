@@ -276,18 +276,30 @@ class B200Model:
             self.metrics_names = ["loss", "positive_loss", "negative_loss", "hard_negative_loss"] + \
                                  (["classification_loss"] if self._classification_loss else [])
 
-    def set_distributed(self, enabled=True):
-        """Data-parallel training: all-reduce the flat gradient buffer over torch.distributed (NCCL)
-        between backward and Adam; every rank keeps identical weights."""
-        if enabled:
-            import torch.distributed as dist
-            if not dist.is_initialized():
-                raise RuntimeError("torch.distributed is not initialised")
-            self._dist = dist
-        else:
+    def set_distributed(self, enabled=True, native=True):
+        """Data-parallel training: every rank keeps identical weights and the flat gradient buffer is summed over
+        the ranks between backward and Adam.  ``native`` (default): the library's own NCCL communicator
+        (``ubd_comm_init`` / ``ubd_allreduce_grads``); ``torch.distributed`` only carries the 128-byte unique id.
+        ``native=False``: all-reduce through ``torch.distributed`` on the raw device buffer."""
+        if not enabled:
             self._dist = None
+            self._native_comm = False
+            return
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dist = dist
+        self._native_comm = bool(native)
+        if native:
+            from .engine import Engine
+            box = [Engine.comm_unique_id() if dist.get_rank() == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self._engine.comm_init(box[0], dist.get_rank(), dist.get_world_size())
 
     def _allreduce_grads(self):
+        if getattr(self, "_native_comm", False):
+            self._engine.allreduce_grads()
+            return 1.0 / self._dist.get_world_size()
         import torch
         ptr, n = self._engine.grad_buffer()
 
