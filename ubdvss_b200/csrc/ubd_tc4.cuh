@@ -435,11 +435,12 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
               }
             }
           } else if (BF16 && out_mode == 0) {
+            // (streaming stores: the next layer reads this map after the whole sweep, long after L2 has turned over)
             uint4* o_px = out + (((size_t)pc.n * h + y) * 3) * wpo + out_pad + x;
 #pragma unroll
             for (int g = 0; g < 3; ++g)
-              o_px[(size_t)g * wpo] = make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
-                                                pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7]));
+              __stcs(o_px + (size_t)g * wpo, make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
+                                                        pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7])));
           } else {
             uint4* o_px = out + (((size_t)pc.n * h + y) * UBD_NG) * wpo + out_pad + x;
             const bool rnd = !BF16 && out_mode == 0;
@@ -447,7 +448,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
             for (int g = 0; g < UBD_NG; ++g) {
               float4 q = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
               if (rnd) { q.x = rna_mma(q.x); q.y = rna_mma(q.y); q.z = rna_mma(q.z); q.w = rna_mma(q.w); }
-              o_px[(size_t)g * wpo] = *reinterpret_cast<uint4*>(&q);
+              __stcs(o_px + (size_t)g * wpo, *reinterpret_cast<uint4*>(&q));
             }
           }
         }
