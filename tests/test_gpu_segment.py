@@ -131,3 +131,27 @@ def test_chunking_does_not_change_results(precision):
         mask, logits, _, comps, counts = o[1:]
         assert np.array_equal(mask, mask0) and np.array_equal(logits, logits0)
         assert np.array_equal(counts, counts0) and np.array_equal(comps["box"], comps0["box"])
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (64 x 1024 x 1024, tf32), checked through size-independent properties: the mask is
+    the strict threshold of the returned logits, components of the fused call equal those of `postprocess` on that
+    mask, and permuting the batch permutes the results (images are independent, model_runner.py:127-134)."""
+    from ubdvss_b200 import _lib
+    from ubdvss_b200.engine import Engine
+    eng = Engine(precision="tf32")
+    eng.set_weights(onet.init_weights(0, seed=1234))
+    base = synth.synth_images(8, 1024, 1024, seed=1)
+    x = np.ascontiguousarray(np.concatenate([base] * 8, 0))
+    thr = float(np.quantile(eng.forward(x[:2], _lib.PREPROC_MOBILENET)[..., 0], 0.9))
+    mask, logits, _, comps, counts = eng.segment(x, thr, 10, _lib.PREPROC_MOBILENET)
+    assert np.array_equal(mask, (logits[..., 0] > np.float32(thr)).astype(np.uint8))
+    _, comps2, counts2 = eng.postprocess(mask, None, 10)
+    assert np.array_equal(counts, counts2) and np.array_equal(comps["box"], comps2["box"])
+    assert np.array_equal(comps["area_x2"], comps2["area_x2"])
+    # the batch is 8 distinct images repeated 8 times: every repeat must reproduce the first block exactly
+    for r in range(1, 8):
+        assert np.array_equal(mask[8 * r:8 * r + 8], mask[:8]) and np.array_equal(logits[8 * r:8 * r + 8], logits[:8])
+    perm = np.random.default_rng(0).permutation(64)
+    mask_p, logits_p, _, comps_p, counts_p = eng.segment(np.ascontiguousarray(x[perm]), thr, 10, _lib.PREPROC_MOBILENET)
+    assert np.array_equal(mask_p, mask[perm]) and np.array_equal(logits_p, logits[perm]) and np.array_equal(counts_p, counts[perm])
