@@ -135,3 +135,22 @@ def test_weight_roundtrip_and_errors():
     with pytest.raises(_lib.UbdError) as e:
         eng.forward(np.zeros((1, 40, 64, 1), np.uint8))       # 40 is not a multiple of 16
     assert e.value.code == -1
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_translation_equivariance_at_full_size(precision):
+    """A fully convolutional net: shifting the image by 64 px shifts the logit map by 16 px wherever the receptive
+    field (< 200 image px) sees neither the seam of the roll nor the border.  At 1024 x 1024 this walks every tap
+    offset, strip boundary and y-phase of the tensor-core kernels; the arithmetic per output is the same, so the
+    match is exact."""
+    w = onet.init_weights(0, seed=5)
+    eng = _engine(precision=precision)
+    eng.set_weights(w)
+    x = synth.synth_images(2, 1024, 1024, seed=9)
+    a = eng.forward(x, _lib.PREPROC_MOBILENET)
+    for dy, dx in ((64, 0), (0, 64), (128, 192)):
+        b = eng.forward(np.ascontiguousarray(np.roll(x, (dy, dx), axis=(1, 2))), _lib.PREPROC_MOBILENET)
+        m = 56                                              # map pixels kept away from borders and the roll seam
+        ref = a[:, m:256 - m - dy // 4, m:256 - m - dx // 4]
+        got = b[:, m + dy // 4:256 - m, m + dx // 4:256 - m]
+        assert np.array_equal(got, ref), (precision, dy, dx, float(np.abs(got - ref).max()))
