@@ -382,6 +382,7 @@ static int ensure_maps(ubd_handle h, int n, int mh, int mw) {
 // the copy stream just ahead of its compute, so the PCIe transfer of chunk k+1 overlaps chunk k.
 static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
                           float* d_logits, uint8_t* d_mask, float thr, const void* h_img = nullptr) {
+  h->loss_pixels = 0;            // the handle's logits are about to be overwritten: ubd_metric_counts needs a new loss batch
   HostTimer ht_fwd(h, 0);
   const int h4 = H / 4, w4 = W / 4;
   const int chunk = pick_chunk(h, n, H, W);
