@@ -230,8 +230,12 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
   const uint32_t slots0 = smem_u32(S.slots);
   if (!L1SRC && w == sw) {
     // single-strip maps: the pad columns of the staged rows are never copied (12 % of the read traffic), so
-    // the slots are cleared once; the MMAs read them through the async proxy
-    for (int i = threadIdx.x; i < NS * S_t::SLOT / 16; i += blockDim.x) reinterpret_cast<uint4*>(S.slots)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // their pad columns are cleared once; the MMAs read them through the async proxy
+    for (int i = threadIdx.x; i < NS * NGI * 2 * PAD; i += blockDim.x) {      // the 2 x 16 pad pixels of every plane of every slot
+      const int pp = i % (2 * PAD), pl = (i / (2 * PAD)) % NGI, sl = i / (2 * PAD * NGI);
+      const int px = pp < PAD ? pp : w + pp;
+      *reinterpret_cast<uint4*>(S.slots + (size_t)sl * S_t::SLOT + ((size_t)pl * (sw + 2 * PAD) + px) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
   }
