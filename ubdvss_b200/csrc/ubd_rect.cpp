@@ -33,7 +33,8 @@ void convex_hull(std::vector<Pt>& pts, std::vector<Pt>& hull) {
   hull.clear();
   const int n = (int)pts.size();
   if (n <= 2) { hull = pts; return; }
-  std::vector<Pt> h(2 * n);
+  static thread_local std::vector<Pt> h;                 // scratch reused across calls (one call per component)
+  h.resize(2 * n);
   int k = 0;
   for (int i = 0; i < n; ++i) {
     while (k >= 2 && cross(h[k - 2], h[k - 1], pts[i]) <= 0) --k;
@@ -59,8 +60,10 @@ struct P2f { float x, y; };
 // Rotating calipers, minimal-area rectangle: out[0] = corner, out[1], out[2] = edge vectors.
 void rotating_calipers(const P2f* points, int n, P2f out[3]) {
   float minarea = 3.402823466e+38f;
-  std::vector<float> inv_vect_length(n);
-  std::vector<P2f> vect(n);
+  static thread_local std::vector<float> inv_vect_length;
+  static thread_local std::vector<P2f> vect;
+  inv_vect_length.resize(n);
+  vect.resize(n);
   int left = 0, bottom = 0, right = 0, top = 0;
   int seq[4];
   float orientation = 0.f, base_a, base_b = 0.f;
@@ -144,13 +147,15 @@ void rotating_calipers(const P2f* points, int n, P2f out[3]) {
 // pts: any superset of the component's hull vertices (e.g. its row-run end points).
 extern "C" int ubd_min_area_box(const int32_t* pts_xy, int n_pts, float* box) {
   if (box == nullptr || (n_pts > 0 && pts_xy == nullptr) || n_pts < 0) return UBD_ERR_ARG;
-  std::vector<Pt> pts(n_pts), hull;
+  static thread_local std::vector<Pt> pts, hull;
+  pts.resize(n_pts);
   for (int i = 0; i < n_pts; ++i) { pts[i].x = pts_xy[2 * i]; pts[i].y = pts_xy[2 * i + 1]; }
   convex_hull(pts, hull);
   const int n = (int)hull.size();
   float cx = 0.f, cy = 0.f, w = 0.f, hgt = 0.f, angle = 0.f;
   if (n > 2) {
-    std::vector<P2f> hp(n);
+    static thread_local std::vector<P2f> hp;
+    hp.resize(n);
     for (int i = 0; i < n; ++i) { hp[i].x = (float)hull[i].x; hp[i].y = (float)hull[i].y; }
     P2f out[3];
     rotating_calipers(hp.data(), n, out);
