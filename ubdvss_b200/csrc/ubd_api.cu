@@ -18,6 +18,7 @@
 #include "ubd_tc.cuh"
 #include "ubd_tc4.cuh"
 #include "ubd_stem_tc.cuh"
+#include "ubd_stemf.cuh"
 #include "ubd_train.cuh"
 
 static std::string g_create_error;
@@ -112,6 +113,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   h->device = device; h->grey = grey != 0; h->fml = fml_compatible != 0; h->n_classes = n_classes;
   h->precision = precision; h->spec = make_weight_spec(grey, n_classes);
   h->n_sm = prop.multiProcessorCount;
+  if (const char* ev = getenv("UBD_STEM_VARIANT")) h->opt_stem_variant = atoi(ev);      // A/B runs of bench.py
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -131,6 +133,8 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   cudaFuncSetAttribute(dilconv_fp32_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 24 * 24 * 4);
   tc_setup_attributes();
   tc4_setup_attributes();
+  stem_setup_attributes();
+  stemf_setup_attributes();
   *out = h;
   return UBD_OK;
 }
@@ -197,6 +201,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
     for (double& v : h->host_ms) v = 0;
   }
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
+  else if (!strcmp(name, "stem_variant")) h->opt_stem_variant = (int)value;
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
   else if (!strcmp(name, "stem_chunk")) h->opt_stem_chunk = (int)value;
   else if (!strcmp(name, "tc_trace")) {
@@ -389,8 +394,8 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
   const int schunk = pick_stem_chunk(h, chunk, H, W, h_img != nullptr);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
   if (h->precision == UBD_FP32) ENSURE(h->act1, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
-  {
-    // plain layout, or split by column parity with x padding (tensor-core stem)
+  if (h->precision == UBD_FP32 || !stem_is_fused(h)) {
+    // plain layout, or split by column parity with x padding (tensor-core stem); the fused stem has no act2
     const size_t plain = (size_t)schunk * UBD_NG * half_px * sizeof(float4);
     const size_t split = (size_t)schunk * (H / 2) * 2 * UBD_NG * (size_t)(W / 4 + 2 * UBD_MAP_PAD) * sizeof(float4);
     const size_t cap0 = h->act2.cap;

@@ -449,17 +449,28 @@ stem3_tc_kernel(const float4* __restrict__ act2, float4* __restrict__ act3, cons
 
 }  // namespace stem
 
+// Function attributes are per device: called from every ubd_create (a second handle on another GPU of the
+// same process must not inherit a "done" flag).
+template <int CIN, typename TIn>
+static void stem12_set_attr() {
+  const int smem = (int)sizeof(stem::Smem12<CIN, TIn>) + 128;
+  cudaFuncSetAttribute(stem::stem12_tc_kernel<CIN, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(stem::stem12_tc_kernel<CIN, TIn>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // 2 CTAs / SM
+}
+static void stem_setup_attributes() {
+  stem12_set_attr<1, uint8_t>(); stem12_set_attr<1, float>(); stem12_set_attr<3, uint8_t>(); stem12_set_attr<3, float>();
+  const int smem3 = (int)sizeof(stem::Smem3) + 128;
+  cudaFuncSetAttribute(stem::stem3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+  cudaFuncSetAttribute(stem::stem3_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(stem::stem3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+  cudaFuncSetAttribute(stem::stem3_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 template <int CIN, typename TIn>
 static int stem12_launch(ubd_handle h, const TIn* img, float4* act2, const float* lut, float ps, float psh,
                          int n, int H, int W, int p2) {
   auto kern = stem::stem12_tc_kernel<CIN, TIn>;
   const size_t smem = sizeof(stem::Smem12<CIN, TIn>) + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // 2 CTAs / SM
-    attr_set = true;
-  }
   const int nitems = n * ((H / 2 + stem::RS - 1) / stem::RS) * ((W / 2 + stem::SEGPX - 1) / stem::SEGPX);
   const int grid = std::min(nitems, 2 * h->n_sm);
   const uint8_t* wb2 = (const uint8_t*)h->stem_wimg.p;
@@ -471,6 +482,11 @@ static int stem12_launch(ubd_handle h, const TIn* img, float4* act2, const float
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
 }
+
+static int stemf_launch(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W, float4* act3);
+
+// Does the fused separable kernel (ubd_stemf.cuh) take this input?  Grey images only (one L1 scalar per pixel).
+static inline bool stem_is_fused(ubd_handle h) { return h->spec.cin == 1 && h->opt_stem_variant == 2; }
 
 // tensor-core stem: image -> act3.  Needs tc_prepare (error flag) and the pointwise B images.
 static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W,
@@ -491,6 +507,7 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
     UBD_CUDA(cudaGetLastError());
     h->stem_weights_dirty = false;
   }
+  if (stem_is_fused(h)) return stemf_launch(h, d_img, in_dtype, preproc, n, H, W, act3);
   const int p2 = stride2_pad(h);
   const bool mob = preproc == UBD_PREPROC_MOBILENET;
   if (h->spec.cin == 1 && in_dtype == UBD_U8 && h->opt_dense_l2) {
@@ -520,14 +537,6 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
   h->act2_tag = 0;                     // plain-layout act2 from here on
   {
     const size_t smem = sizeof(stem::Smem3) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(stem::stem3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(stem::stem3_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(stem::stem3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(stem::stem3_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set = true;
-    }
     const int H2 = H / 2, W2 = W / 2;
     const int ntiles = n * ((H2 / 2 + stem::R3 - 1) / stem::R3) * ((W2 / 2 + stem::SEGPX - 1) / stem::SEGPX);
     const int grid = std::min(ntiles, 3 * h->n_sm);
