@@ -154,3 +154,26 @@ def test_translation_equivariance_at_full_size(precision):
         ref = a[:, m:256 - m - dy // 4, m:256 - m - dx // 4]
         got = b[:, m + dy // 4:256 - m, m + dx // 4:256 - m]
         assert np.array_equal(got, ref), (precision, dy, dx, float(np.abs(got - ref).max()))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("fml", [True, False])
+def test_fused_stem_kernel(fml, precision):
+    """ubd_stemf.cuh (image -> L1 -> L2 -> L3 in one launch, no half-resolution map in HBM) forced for uint8
+    input (option stem_variant 2; float input takes it by default): same bounds as the default path, on
+    ragged shapes (partial strips / bands), several strips per row and the class head."""
+    for n_classes, shape in [(0, (2, 48, 80)), (6, (3, 64, 192)), (0, (1, 272, 1040)), (0, (2, 1024, 1024))]:
+        w = onet.init_weights(n_classes, seed=7)
+        eng = _engine(fml_compatible=fml, n_classes=n_classes, precision=precision)
+        eng.set_weights(w)
+        eng.set_option("stem_variant", 2)
+        x = synth.synth_images(*shape, seed=11)
+        got, _ = _check(eng, w, x, _lib.PREPROC_MOBILENET, fml=fml, precision=precision)
+        _check(eng, w, x, _lib.PREPROC_NONE, fml=fml, precision=precision)
+        # float input through the same kernel (TIn = float): bit-identical to the uint8 + table path
+        xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
+        assert np.array_equal(eng.forward(xf, _lib.PREPROC_NONE), got)
+        # the two-kernel stem stays within the stated bound of it (tf32: different rounding points)
+        eng.set_option("stem_variant", 1)
+        ref2 = eng.forward(x, _lib.PREPROC_MOBILENET)
+        assert np.abs(_sig(ref2[..., 0]) - _sig(got[..., 0])).max() <= 2 * PROB_TOL[precision]

@@ -394,7 +394,7 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
   const int schunk = pick_stem_chunk(h, chunk, H, W, h_img != nullptr);
   const size_t half_px = (size_t)(H / 2) * (W / 2), q_px = (size_t)h4 * w4;
   if (h->precision == UBD_FP32) ENSURE(h->act1, (size_t)schunk * UBD_NG * half_px * sizeof(float4));
-  if (h->precision == UBD_FP32 || !stem_is_fused(h)) {
+  if (h->precision == UBD_FP32 || !stem_is_fused(h, in_dtype)) {
     // plain layout, or split by column parity with x padding (tensor-core stem); the fused stem has no act2
     const size_t plain = (size_t)schunk * UBD_NG * half_px * sizeof(float4);
     const size_t split = (size_t)schunk * (H / 2) * 2 * UBD_NG * (size_t)(W / 4 + 2 * UBD_MAP_PAD) * sizeof(float4);

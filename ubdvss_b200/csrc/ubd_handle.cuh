@@ -33,7 +33,7 @@ struct ubd_handle_s {
   bool tc4_weights_dirty = true;  // ... the column-rotating kernel's weight images (ubd_tc4.cuh)
   int opt_tc_variant = 1;         // dilated layers: 1 = ubd_tc4.cuh, 0 = ubd_tc.cuh (see launch_dil_tc)
 
-  int opt_stem_variant = 2;       // grey input: 2 = fused separable kernel (ubd_stemf.cuh), else the two-kernel paths below
+  int opt_stem_variant = 0;       // grey input: 2 = fused separable kernel (ubd_stemf.cuh), 1 = two-kernel paths, 0 = auto (stem_is_fused)
   int opt_dense_l2 = 1;           // stem L2 as dense tensor-core conv for grey uint8 input (0: FP32-pipe depthwise path)
   int opt_stem_chunk = 0;         // images per stem launch (0 = auto)
   int opt_chunk = 0;              // images per L2-resident chunk (0 = auto)

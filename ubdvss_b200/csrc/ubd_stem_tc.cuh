@@ -486,7 +486,13 @@ static int stem12_launch(ubd_handle h, const TIn* img, float4* act2, const float
 static int stemf_launch(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W, float4* act3);
 
 // Does the fused separable kernel (ubd_stemf.cuh) take this input?  Grey images only (one L1 scalar per pixel).
-static inline bool stem_is_fused(ubd_handle h) { return h->spec.cin == 1 && h->opt_stem_variant == 2; }
+// opt_stem_variant: 2 = always; 1 = never; 0 (auto) = for float input - uint8 input takes the dense tcgen05 pair
+// (L1+L2 dense, L3 dense), measured 1.035 ms vs 1.07 ms per 64 x 1024^2 on B200 although it round-trips the
+// half-resolution map through HBM (profiles/r02_stem_summary.md).
+static inline bool stem_is_fused(ubd_handle h, int in_dtype) {
+  if (h->spec.cin != 1 || h->opt_stem_variant == 1) return false;
+  return h->opt_stem_variant == 2 || in_dtype != UBD_U8;
+}
 
 // tensor-core stem: image -> act3.  Needs tc_prepare (error flag) and the pointwise B images.
 static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W,
@@ -507,7 +513,7 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
     UBD_CUDA(cudaGetLastError());
     h->stem_weights_dirty = false;
   }
-  if (stem_is_fused(h)) return stemf_launch(h, d_img, in_dtype, preproc, n, H, W, act3);
+  if (stem_is_fused(h, in_dtype)) return stemf_launch(h, d_img, in_dtype, preproc, n, H, W, act3);
   const int p2 = stride2_pad(h);
   const bool mob = preproc == UBD_PREPROC_MOBILENET;
   if (h->spec.cin == 1 && in_dtype == UBD_U8 && h->opt_dense_l2) {

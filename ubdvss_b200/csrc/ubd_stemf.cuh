@@ -29,7 +29,7 @@ constexpr int BH = 16;                        // act3 rows per work item
 constexpr int A_PLANE = SW2 * 16;             // 2048 B: one channel plane of an A tile
 constexpr int A_TILE = UBD_NG * A_PLANE;      // 12288 B
 constexpr int SC_RING = 8, SC_PITCH = 132;    // L1 scalar rows (130 columns feed 128 L2 columns)
-constexpr int IMG_RING = 8, IMG_HALF = 132;   // preprocessed image rows, even / odd patch columns
+constexpr int IMG_RING = 8, IMG_PITCH = 272;  // preprocessed image rows (floats), element 0 = the word-aligned patch start
 constexpr int IMG_COLS = 2 * (SW2 + 2) + 1;   // 261 image columns feed 130 L1 columns
 constexpr int R2_PITCH = 134;                 // float4 per (slot, plane): A[0..64] then B[0..63] at offset 68 / 69
 constexpr int R2_SLOT = UBD_NG * R2_PITCH;    // float4 per ring row
@@ -42,11 +42,10 @@ struct Smem {
   float4 r2[3 * R2_SLOT];                     // L2 rows (post-ReLU), ring of 3, parity split
   float4 carry[2][CARRY_ROWS * UBD_NG];       // L2 column handed to the next strip (double-buffered by strip)
   uint8_t wimg2[stem::PW_IMG_BYTES], wimg3[stem::PW_IMG_BYTES];
-  float imgE[IMG_RING * IMG_HALF], imgO[IMG_RING * IMG_HALF];
-  float sc[SC_RING * SC_PITCH];
+  __align__(16) float imgp[IMG_RING * IMG_PITCH];
+  __align__(16) float sc[2 * SC_RING * SC_PITCH];   // L1 sums, each stored twice (fp32x2 operand)
   __align__(16) float dw2[9 * UBD_NF];
   __align__(16) float dw3[9 * UBD_NF];
-  __align__(16) float zeros[9 * UBD_NF];
   __align__(16) float b2[32], b3[32];
   __align__(16) float pw1[UBD_NF], b1[UBD_NF];
   float dw1[12], lut[256];
@@ -72,7 +71,35 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, int* ge
   tc::tc_fence_after();
 }
 
+// packed fp32x2 arithmetic (sm_100: one FFMA2 / FADD2 / FMUL2 issue slot for two lanes of work)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 relu2(float2 a) { return make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); }
+__device__ __forceinline__ float2 rna2(float2 a) { return make_float2(rna_bits(a.x), rna_bits(a.y)); }
+
 // OUT_MODE 1: fp32 planes rounded to the tf32 grid; 2: bf16, 3 planes of 8 channels.
+//
+// Thread roles inside a step (256 threads):
+//   L2 depthwise : thread = (pixel pair pp = tid & 63 -> strip pixels 2pp, 2pp+1; channel group tid >> 6 -> 6 channels
+//                  as 3 fp32x2 pairs).  The two pixels share their four L1 columns, so a rebuilt L1 value feeds
+//                  both; M row of pixel px in the A tile / TMEM lane: m = (px & 1) * 64 + (px >> 1), which makes
+//                  both the A-tile stores here and the parity-split ring stores of the epilogue unit-stride.
+//   L3 depthwise : three (pixel j = tid & 63, channel pair) outputs per thread.
+//   epilogues    : warp w -> L2 row (w >> 2), TMEM quadrant (w & 3); the act3 row goes to warps 0,1,4,5 (12 channels each).
 template <typename TIn, int OUT_MODE>
 __global__ void __launch_bounds__(THREADS, 2)
 stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const float* __restrict__ params,
@@ -82,8 +109,9 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
                   int N, int H, int W, int p2, int* __restrict__ work_counter, int* gerr) {
   constexpr int ELT = (int)sizeof(TIn);
   constexpr int EPQ = 4 / ELT;                                   // elements per 4-byte word
-  constexpr int QUADS = (IMG_COLS * ELT + 3) / 4 + 1;            // words covering one patch row
+  constexpr int QUADS = ELT == 1 ? (IMG_COLS + 3 + 3) / 4 : IMG_COLS;    // words covering one patch row (u8: word-floored start)
   constexpr int NW = (4 * QUADS + THREADS - 1) / THREADS;        // words per thread for the 4 new image rows of a step
+  static_assert(QUADS * EPQ <= IMG_PITCH, "image ring pitch");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,7 +119,7 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
 
   for (int i = tid; i < 9; i += THREADS) S.dw1[i] = params[off_dw1 + i];
   for (int i = tid; i < UBD_NF; i += THREADS) { S.pw1[i] = params[off_pw1 + i]; S.b1[i] = params[off_b1 + i]; }
-  for (int i = tid; i < 9 * UBD_NF; i += THREADS) { S.dw2[i] = params[off_dw2 + i]; S.dw3[i] = params[off_dw3 + i]; S.zeros[i] = 0.f; }
+  for (int i = tid; i < 9 * UBD_NF; i += THREADS) { S.dw2[i] = params[off_dw2 + i]; S.dw3[i] = params[off_dw3 + i]; }
   for (int i = tid; i < 256; i += THREADS) S.lut[i] = lut ? lut[i] : (float)i;
   for (int i = tid; i < stem::PW_IMG_BYTES / 4; i += THREADS) {
     reinterpret_cast<float*>(S.wimg2)[i] = __ldg(reinterpret_cast<const float*>(wb2) + i);
@@ -118,20 +146,21 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
   const uint32_t tmem_base = S.tmem_base;
 
   // ---- per-thread constants
-  const int px = tid & (SW2 - 1);                                // L2 depthwise: pixel column of the strip
-  const int gb = (tid >> 7) * 3;                                 // ... and its three channel planes
-  float pw1r[12], b1r[12];
-#pragma unroll
-  for (int c = 0; c < 12; ++c) { pw1r[c] = S.pw1[4 * gb + c]; b1r[c] = S.b1[4 * gb + c]; }
-  float dw1r[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) dw1r[i] = S.dw1[i];
+  const int pp = tid & 63, qg = tid >> 6;                        // L2 depthwise: pixel pair, channel group (pairs 3qg .. 3qg+2)
+  // A2 byte offset of channel pair 3qg (even pixel -> M row pp, odd pixel -> M row 64 + pp); pair c2 lives at
+  // plane c2 >> 1, half c2 & 1: consecutive pairs are 8 bytes apart inside a plane, else A_PLANE - 8
   const int row_bytes_img = W * ELT;
   const int boff = p2 ? 69 : 68;                                 // bank-conflict-free parity split for this padding mode
   const int ns = (W4 + SW3 - 1) / SW3;
   const int nbands = (H4 + BH - 1) / BH;
   const int nitems = N * nbands;
   uint32_t mma_count = 0;
+  // image words of a step: word slot k of this thread = (row r_k of the 4 new rows, word q_k of the patch row)
+  int wr_[NW], wq_[NW];
+#pragma unroll
+  for (int k = 0; k < NW; ++k) { const int idx = tid + k * THREADS; wr_[k] = idx < 4 * QUADS ? idx / QUADS : -1; wq_[k] = idx % QUADS; }
+  // L1 sums of a step: (row, column) of the two new rows
+  const int sc_r0 = tid / (SW2 + 2), sc_c0 = tid % (SW2 + 2);    // second task (tid < 4): row 1, column 126 + tid
 
   const uint32_t a2_0 = ((tc::smem_u32(S.A2) >> 4) & 0x3FFFu) | (((uint32_t)A_PLANE >> 4) << 16);
   const uint32_t a3_0 = ((tc::smem_u32(S.A3) >> 4) & 0x3FFFu) | (((uint32_t)A_PLANE >> 4) << 16);
@@ -158,54 +187,58 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
       const int b0 = ix0 * ELT;
       const int a0 = b0 >= 0 ? (b0 & ~3) : -(((-b0) + 3) & ~3);  // floored to a word
       const int e0 = (a0 - b0) / ELT;                            // patch element index of word 0 (<= 0)
+      const int eoff = -e0;                                      // ring element of patch column 0
+      // per-strip constants of this thread's image words: is the word inside the row, its address in image row 0
+      bool wok[NW];
+      const uint8_t* wp[NW];
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const int off = a0 + 4 * wq_[k];
+        wok[k] = wr_[k] >= 0 && off >= 0 && off < row_bytes_img;
+        wp[k] = img_n + off;
+      }
       auto load_word = [&](int iy, int q) -> uint32_t {
         const int off = a0 + 4 * q;
         if (iy < 0 || iy >= H || off < 0 || off >= row_bytes_img) return 0u;
         return __ldg(reinterpret_cast<const uint32_t*>(img_n + (size_t)iy * row_bytes_img + off));
       };
-      auto store_word = [&](uint32_t v, int iy, int q) {
-        const int off = a0 + 4 * q;
-        const bool inside = iy >= 0 && iy < H && off >= 0 && off < row_bytes_img;
-        const int slot = iy & (IMG_RING - 1);
-        const TIn* e = reinterpret_cast<const TIn*>(&v);
-#pragma unroll
-        for (int k = 0; k < EPQ; ++k) {
-          const int col = e0 + q * EPQ + k;
-          if ((unsigned)col >= (unsigned)IMG_COLS) continue;
+      // word q of image row iy -> ring (zeros outside the image): uint8: four table look-ups, one 16-byte store
+      auto store_word = [&](uint32_t v, int iy, bool inside, int q) {
+        float* dst = &S.imgp[(iy & (IMG_RING - 1)) * IMG_PITCH + q * EPQ];
+        if constexpr (sizeof(TIn) == 1) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (inside) f = make_float4(S.lut[v & 0xFFu], S.lut[(v >> 8) & 0xFFu], S.lut[(v >> 16) & 0xFFu], S.lut[v >> 24]);
+          *reinterpret_cast<float4*>(dst) = f;
+        } else {
           float f = 0.f;
-          if (inside) {
-            if constexpr (sizeof(TIn) == 1) f = S.lut[(int)e[k]];
-            else { f = (float)e[k]; if (pre_scale != 0.f) f = (f - pre_shift) / pre_scale; }
-          }
-          ((col & 1) ? S.imgO : S.imgE)[slot * IMG_HALF + (col >> 1)] = f;
+          if (inside) { f = __uint_as_float(v); if (pre_scale != 0.f) f = (f - pre_shift) / pre_scale; }
+          *dst = f;
         }
       };
-      // L1 depthwise sum of map pixel (yy, local column c); rows outside the map are never read
+      // L1 depthwise sum of map pixel (yy, local column c), stored twice (fp32x2 operand); rows outside the map are never read
       auto l1_scalar = [&](int yy, int c) {
         float a = 0.f;
 #pragma unroll
         for (int ti = 0; ti < 3; ++ti) {
-          const int slot = (2 * yy - p2 + ti) & (IMG_RING - 1);
-          const float* E = &S.imgE[slot * IMG_HALF + c];
-          const float* O = &S.imgO[slot * IMG_HALF + c];
-          a = fmaf(E[0], dw1r[ti * 3 + 0], a);
-          a = fmaf(O[0], dw1r[ti * 3 + 1], a);
-          a = fmaf(E[1], dw1r[ti * 3 + 2], a);
+          const float* r = &S.imgp[((2 * yy - p2 + ti) & (IMG_RING - 1)) * IMG_PITCH + eoff + 2 * c];
+          a = fmaf(r[0], S.dw1[ti * 3 + 0], a);
+          a = fmaf(r[1], S.dw1[ti * 3 + 1], a);
+          a = fmaf(r[2], S.dw1[ti * 3 + 2], a);
         }
-        S.sc[(yy & (SC_RING - 1)) * SC_PITCH + c] = a;
+        reinterpret_cast<float2*>(S.sc)[(yy & (SC_RING - 1)) * SC_PITCH + c] = make_float2(a, a);
       };
-      // column validity of this thread's three L1 columns (zero padding of L2's input in x)
-      const int xg = X2 + px;
-      const float4* wl = reinterpret_cast<const float4*>((xg - 1 >= 0 && xg - 1 < W2) ? S.dw2 : S.zeros);
-      const float4* wc = reinterpret_cast<const float4*>((xg < W2) ? S.dw2 : S.zeros);
-      const float4* wr = reinterpret_cast<const float4*>((xg + 1 < W2) ? S.dw2 : S.zeros);
+      // zero padding of L2's input in x: only the column left of pixel 2pp and the one right of 2pp+1 can be outside
+      const float m0f = (X2 + 2 * pp - 1 >= 0) ? 1.f : 0.f, m3f = (X2 + 2 * pp + 2 < W2) ? 1.f : 0.f;
+      const float2 m0 = make_float2(m0f, m0f), m3 = make_float2(m3f, m3f);
 
       // ---- prologue: image rows of L1 rows r0-1 .. r0+1, then those L1 sums
       {
         const int iyA = 2 * (r0 - 1) - p2;
         for (int i = tid; i < 7 * QUADS; i += THREADS) {
           const int r = i / QUADS, q = i - r * QUADS;
-          store_word(load_word(iyA + r, q), iyA + r, q);
+          const int off = a0 + 4 * q;
+          const bool inside = iyA + r >= 0 && iyA + r < H && off >= 0 && off < row_bytes_img;
+          store_word(load_word(iyA + r, q), iyA + r, inside, q);
         }
         __syncthreads();
         for (int i = tid; i < 3 * (SW2 + 2); i += THREADS) {
@@ -222,102 +255,96 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
         const bool next_l2 = i + 1 <= nrows3;
         const int q = r0 + 2 * i + 2;                            // L1 rows q, q+1 are summed in this step for the next one
         // (1) issue the loads of the four image rows those sums add
-        uint32_t wq[NW];
+        uint32_t wv[NW];
         const int iyN = 2 * q - p2 + 1;
         if (next_l2) {
 #pragma unroll
           for (int k = 0; k < NW; ++k) {
-            const int idx = tid + k * THREADS;
-            wq[k] = idx < 4 * QUADS ? load_word(iyN + idx / QUADS, idx % QUADS) : 0u;
+            const int iy = iyN + wr_[k];
+            wv[k] = (wok[k] && (unsigned)iy < (unsigned)H) ? __ldg(reinterpret_cast<const uint32_t*>(wp[k] + (size_t)iy * row_bytes_img)) : 0u;
           }
         }
         // (2) L2 depthwise of the step's rows -> A2 tiles
         if (nL2 > 0) {
           const int rowA = r0 + relA;
-          float sv[4][3];
+          float4 sv[4][2];                                       // L1 sums of columns 2pp-1 .. 2pp+2, each duplicated
           bool rv[4];
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
             const int y = rowA - 1 + rr;
             rv[rr] = rr < nL2 + 2 && y >= 0 && y < H2;
             if (rv[rr]) {
-              const float* sp = &S.sc[(y & (SC_RING - 1)) * SC_PITCH + px];
-              sv[rr][0] = sp[0]; sv[rr][1] = sp[1]; sv[rr][2] = sp[2];
+              const float4* sp = reinterpret_cast<const float4*>(S.sc) + ((y & (SC_RING - 1)) * SC_PITCH >> 1) + pp;
+              sv[rr][0] = sp[0]; sv[rr][1] = sp[1];
             } else {
-              sv[rr][0] = sv[rr][1] = sv[rr][2] = 0.f;
+              sv[rr][0] = sv[rr][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const int g = gb + k;
-            float4 wt[9];
+            const float2* w2 = reinterpret_cast<const float2*>(S.dw2) + (3 * qg + k);     // [tap][12 pairs]
+            const float2 pwk = reinterpret_cast<const float2*>(S.pw1)[3 * qg + k], b1k = reinterpret_cast<const float2*>(S.b1)[3 * qg + k];
+            float2 w[9], wl[3], wrr[3];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) wt[t] = (t % 3 == 0 ? wl : (t % 3 == 1 ? wc : wr))[t * UBD_NG + g];
-            float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+            for (int t = 0; t < 9; ++t) w[t] = w2[t * 12];
+#pragma unroll
+            for (int ti = 0; ti < 3; ++ti) { wl[ti] = fmul2(w[ti * 3], m0); wrr[ti] = fmul2(w[ti * 3 + 2], m3); }
+            float2 acc[2][2];
+            acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
               if (!rv[rr]) continue;
-              float4 a[3];
-#pragma unroll
-              for (int tj = 0; tj < 3; ++tj) {
-                a[tj].x = fmaxf(fmaf(sv[rr][tj], pw1r[4 * k + 0], b1r[4 * k + 0]), 0.f);
-                a[tj].y = fmaxf(fmaf(sv[rr][tj], pw1r[4 * k + 1], b1r[4 * k + 1]), 0.f);
-                a[tj].z = fmaxf(fmaf(sv[rr][tj], pw1r[4 * k + 2], b1r[4 * k + 2]), 0.f);
-                a[tj].w = fmaxf(fmaf(sv[rr][tj], pw1r[4 * k + 3], b1r[4 * k + 3]), 0.f);
-              }
+              float2 a[4];
+              a[0] = relu2(ffma2(make_float2(sv[rr][0].x, sv[rr][0].y), pwk, b1k));
+              a[1] = relu2(ffma2(make_float2(sv[rr][0].z, sv[rr][0].w), pwk, b1k));
+              a[2] = relu2(ffma2(make_float2(sv[rr][1].x, sv[rr][1].y), pwk, b1k));
+              a[3] = relu2(ffma2(make_float2(sv[rr][1].z, sv[rr][1].w), pwk, b1k));
               if (rr < 3) {
-#pragma unroll
-                for (int tj = 0; tj < 3; ++tj) {
-                  const float4 w = wt[rr * 3 + tj];
-                  acc0.x = fmaf(a[tj].x, w.x, acc0.x); acc0.y = fmaf(a[tj].y, w.y, acc0.y);
-                  acc0.z = fmaf(a[tj].z, w.z, acc0.z); acc0.w = fmaf(a[tj].w, w.w, acc0.w);
-                }
+                acc[0][0] = ffma2(a[0], wl[rr], ffma2(a[1], w[rr * 3 + 1], ffma2(a[2], w[rr * 3 + 2], acc[0][0])));
+                acc[0][1] = ffma2(a[1], w[rr * 3], ffma2(a[2], w[rr * 3 + 1], ffma2(a[3], wrr[rr], acc[0][1])));
               }
               if (rr >= 1) {
-#pragma unroll
-                for (int tj = 0; tj < 3; ++tj) {
-                  const float4 w = wt[(rr - 1) * 3 + tj];
-                  acc1.x = fmaf(a[tj].x, w.x, acc1.x); acc1.y = fmaf(a[tj].y, w.y, acc1.y);
-                  acc1.z = fmaf(a[tj].z, w.z, acc1.z); acc1.w = fmaf(a[tj].w, w.w, acc1.w);
-                }
+                acc[1][0] = ffma2(a[0], wl[rr - 1], ffma2(a[1], w[(rr - 1) * 3 + 1], ffma2(a[2], w[(rr - 1) * 3 + 2], acc[1][0])));
+                acc[1][1] = ffma2(a[1], w[(rr - 1) * 3], ffma2(a[2], w[(rr - 1) * 3 + 1], ffma2(a[3], wrr[rr - 1], acc[1][1])));
               }
             }
-            reinterpret_cast<float4*>(S.A2 + g * A_PLANE)[px] =
-                make_float4(rna_bits(acc0.x), rna_bits(acc0.y), rna_bits(acc0.z), rna_bits(acc0.w));
-            if (nL2 == 2)
-              reinterpret_cast<float4*>(S.A2 + A_TILE + g * A_PLANE)[px] =
-                  make_float4(rna_bits(acc1.x), rna_bits(acc1.y), rna_bits(acc1.z), rna_bits(acc1.w));
+            // channel pair 3qg + k of both pixels -> A2 (8-byte stores, unit-stride in M across the warp)
+            const int c2 = 3 * qg + k;
+            uint8_t* dst = S.A2 + (c2 >> 1) * A_PLANE + (c2 & 1) * 8 + pp * 16;
+            *reinterpret_cast<float2*>(dst) = rna2(acc[0][0]);
+            *reinterpret_cast<float2*>(dst + 64 * 16) = rna2(acc[0][1]);
+            if (nL2 == 2) {
+              *reinterpret_cast<float2*>(dst + A_TILE) = rna2(acc[1][0]);
+              *reinterpret_cast<float2*>(dst + A_TILE + 64 * 16) = rna2(acc[1][1]);
+            }
           }
         }
         // (3) L3 depthwise (stride 2) of act3 row Y0 + i - 2 from the ring -> A3 tile
-        if (hasL3 && tid < 3 * SW3) {
-          const int j = tid & (SW3 - 1), pp = tid >> 6;
+        if (hasL3) {
+          const int j = pp;
           const int rel0 = 2 * (i - 2);                          // ring rows rel0 .. rel0 + 2
+          const float2* ring = reinterpret_cast<const float2*>(S.r2);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int g = 2 * pp + k;
-            const float4* w4 = reinterpret_cast<const float4*>(S.dw3) + g;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < 3; ++r) {
+            const int c2 = qg + 4 * r, g = c2 >> 1, hf = c2 & 1;
+            const float2* w2 = reinterpret_cast<const float2*>(S.dw3) + c2;
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ti = 0; ti < 3; ++ti) {
-              const float4* row = &S.r2[((rel0 + ti) % 3) * R2_SLOT + g * R2_PITCH];
-              const float4 v0 = row[j], v1 = row[boff + j], v2 = row[j + 1];
-              const float4 w0 = w4[(ti * 3 + 0) * UBD_NG], w1 = w4[(ti * 3 + 1) * UBD_NG], w2 = w4[(ti * 3 + 2) * UBD_NG];
-              acc.x = fmaf(v0.x, w0.x, fmaf(v1.x, w1.x, fmaf(v2.x, w2.x, acc.x)));
-              acc.y = fmaf(v0.y, w0.y, fmaf(v1.y, w1.y, fmaf(v2.y, w2.y, acc.y)));
-              acc.z = fmaf(v0.z, w0.z, fmaf(v1.z, w1.z, fmaf(v2.z, w2.z, acc.z)));
-              acc.w = fmaf(v0.w, w0.w, fmaf(v1.w, w1.w, fmaf(v2.w, w2.w, acc.w)));
+              const float2* row = ring + ((((rel0 + ti) % 3) * R2_SLOT + g * R2_PITCH) << 1) + hf;
+              const float2 v0 = row[2 * j], v1 = row[2 * (boff + j)], v2 = row[2 * (j + 1)];
+              acc = ffma2(v0, w2[(ti * 3 + 0) * 12], ffma2(v1, w2[(ti * 3 + 1) * 12], ffma2(v2, w2[(ti * 3 + 2) * 12], acc)));
             }
-            reinterpret_cast<float4*>(S.A3 + g * A_PLANE)[j] =
-                make_float4(rna_bits(acc.x), rna_bits(acc.y), rna_bits(acc.z), rna_bits(acc.w));
+            *reinterpret_cast<float2*>(S.A3 + g * A_PLANE + j * 16 + hf * 8) = rna2(acc);
           }
         }
         // (4) the image words of (1) have arrived: preprocess into the ring
         if (next_l2) {
 #pragma unroll
           for (int k = 0; k < NW; ++k) {
-            const int idx = tid + k * THREADS;
-            if (idx < 4 * QUADS) store_word(wq[k], iyN + idx / QUADS, idx % QUADS);
+            if (wr_[k] < 0) continue;
+            const int iy = iyN + wr_[k];
+            store_word(wv[k], iy, wok[k] && (unsigned)iy < (unsigned)H, wq_[k]);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -342,10 +369,8 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
         }
         // (6) L1 sums of rows q, q+1 (next step's new input rows) while the MMAs run
         if (next_l2) {
-          for (int idx = tid; idx < 2 * (SW2 + 2); idx += THREADS) {
-            const int yy = q + idx / (SW2 + 2);
-            if (yy >= 0 && yy < H2) l1_scalar(yy, idx % (SW2 + 2));
-          }
+          if (q + sc_r0 >= 0 && q + sc_r0 < H2) l1_scalar(q + sc_r0, sc_c0);
+          if (tid < 2 * (SW2 + 2) - THREADS && q + 1 >= 0 && q + 1 < H2) l1_scalar(q + 1, THREADS - (SW2 + 2) + tid);
         }
         // (7) epilogues
         wait_bar(&S.mma_bar, mma_count & 1, gerr);
@@ -364,17 +389,22 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
                        : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
                        : "r"(taddr + 16));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int p = quad * 32 + lane;                        // L2 pixel of the strip
+          const int m = quad * 32 + lane;                        // M row -> strip pixel
+          const int p = 2 * (m & 63) + (m >> 6);
           const bool inside = y2 >= 0 && y2 < H2 && X2 + p < W2;
           float4 o[UBD_NG];
+          const float2* b2p = reinterpret_cast<const float2*>(S.b2);
 #pragma unroll
           for (int g = 0; g < UBD_NG; ++g) {
-            o[g].x = inside ? fmaxf(__uint_as_float(v[4 * g + 0]) + S.b2[4 * g + 0], 0.f) : 0.f;
-            o[g].y = inside ? fmaxf(__uint_as_float(v[4 * g + 1]) + S.b2[4 * g + 1], 0.f) : 0.f;
-            o[g].z = inside ? fmaxf(__uint_as_float(v[4 * g + 2]) + S.b2[4 * g + 2], 0.f) : 0.f;
-            o[g].w = inside ? fmaxf(__uint_as_float(v[4 * g + 3]) + S.b2[4 * g + 3], 0.f) : 0.f;
+            const float2 lo = relu2(fadd2(make_float2(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), b2p[2 * g]));
+            const float2 hi = relu2(fadd2(make_float2(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])), b2p[2 * g + 1]));
+            o[g] = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
-          const int idx = p + p2;
+          if (!inside) {
+#pragma unroll
+            for (int g = 0; g < UBD_NG; ++g) o[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const int idx = p + p2;                                // parity is uniform per warp (quadrants 0,1: even pixels)
           float4* dst = &S.r2[(rel % 3) * R2_SLOT + ((idx & 1) ? boff + (idx >> 1) : (idx >> 1))];
 #pragma unroll
           for (int g = 0; g < UBD_NG; ++g) dst[g * R2_PITCH] = o[g];
@@ -389,34 +419,39 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
             for (int g = 0; g < UBD_NG; ++g) cd[g * R2_PITCH] = si == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : carry_in[rel * UBD_NG + g];
           }
         }
-        if (hasL3 && (warp == 4 || warp == 5)) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + 2 * tc::UMMA_N;
-          uint32_t v[24];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                       : "r"(taddr));
+        if (hasL3 && quad < 2) {
+          // act3 row: quadrant = 32 pixels, warp >> 2 = channels 0..11 / 12..23
+          const int ch = warp >> 2;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + 2 * tc::UMMA_N + 12 * ch;
+          uint32_t v[12];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
-                       : "r"(taddr + 16));
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(taddr));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11])
+                       : "r"(taddr + 8));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int j = quad * 32 + lane;
           if (j < w3s) {
             const int y3 = Y0 + i - 2, x3 = s * SW3 + j;
-            float o[UBD_NF];
+            float o[12];
 #pragma unroll
-            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + S.b3[c], 0.f);
+            for (int c = 0; c < 12; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + S.b3[12 * ch + c], 0.f);
             if constexpr (OUT_MODE == 2) {
+              // bf16 planes hold 8 channels: channels 0..11 = plane 0 + low half of plane 1, 12..23 = high half + plane 2
               uint4* dst = reinterpret_cast<uint4*>(act3) + (((size_t)n * H4 + y3) * tc::NG_BF16) * (size_t)(W4 + 2 * UBD_MAP_PAD) + UBD_MAP_PAD + x3;
-#pragma unroll
-              for (int g = 0; g < tc::NG_BF16; ++g)
-                dst[(size_t)g * (W4 + 2 * UBD_MAP_PAD)] =
-                    make_uint4(tc::pack_bf16x2(o[8 * g], o[8 * g + 1]), tc::pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                               tc::pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), tc::pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+              const size_t ps = (size_t)(W4 + 2 * UBD_MAP_PAD);
+              if (ch == 0) {
+                dst[0] = make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
+                *reinterpret_cast<uint2*>(dst + ps) = make_uint2(tc::pack_bf16x2(o[8], o[9]), tc::pack_bf16x2(o[10], o[11]));
+              } else {
+                *(reinterpret_cast<uint2*>(dst + ps) + 1) = make_uint2(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]));
+                dst[2 * ps] = make_uint4(tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]), tc::pack_bf16x2(o[8], o[9]), tc::pack_bf16x2(o[10], o[11]));
+              }
             } else {
 #pragma unroll
-              for (int g = 0; g < UBD_NG; ++g)
-                act3[act_index(n, g, y3, x3, H4, W4, UBD_MAP_PAD)] =
+              for (int g = 0; g < 3; ++g)
+                act3[act_index(n, 3 * ch + g, y3, x3, H4, W4, UBD_MAP_PAD)] =
                     make_float4(rna_bits(o[4 * g]), rna_bits(o[4 * g + 1]), rna_bits(o[4 * g + 2]), rna_bits(o[4 * g + 3]));
             }
           }
