@@ -184,6 +184,20 @@ def hull_points(labels, label):
     return np.array(lo[:-1] + up[:-1], dtype=np.int32)
 
 
+def is_equal_area_tie(box_a, box_b, rel=2e-6) -> bool:
+    """True when two rounded rotated boxes are different rectangles of the same area: the only residue between
+    the library and cv2.minAreaRect (a float32 tie between calipers positions whose winner depends on where
+    cv2's convexHull starts, which in turn depends on duplicated points of the traced contour; observed once
+    in 15,062 kept components)."""
+    def area_perimeter(b):
+        b = np.asarray(b, np.float64).reshape(4, 2)            # boxPoints order: consecutive corners are adjacent
+        u, v = np.linalg.norm(b[1] - b[0]), np.linalg.norm(b[2] - b[1])
+        return u * v, 2 * (u + v)
+    (a, pa), (b, pb) = area_perimeter(box_a), area_perimeter(box_b)
+    # corners are rounded to integers (x4 units): each side moves by < 1, the area by < perimeter / 2 + 1
+    return abs(a - b) <= rel * max(a, b) + 0.5 * max(pa, pb) + 1.0
+
+
 def boxes_equivalent(box_a, box_b, tol=0) -> bool:
     """Rotated boxes compared as corner SETS (corner order is OpenCV-version dependent, P3)."""
     a = sorted(map(tuple, np.asarray(box_a).reshape(4, 2).tolist()))

@@ -40,7 +40,7 @@ def test_model_runner_predict_matches_reference_golden(golden, thr, mode):
     assert [len(f) for f in found] == list(golden[f"{key}_counts"])
     boxes = [o.bbox for f in found for o in f]
     bad = sum(not pp.boxes_equivalent(b, g) for b, g in zip(boxes, golden[f"{key}_boxes"]))
-    assert bad <= 1
+    assert bad == 0
     if mode == "cls":
         assert [o.object_type for f in found for o in f] == list(golden[f"{key}_classes"])
 
@@ -71,7 +71,7 @@ def test_end_to_end_against_oracle(n_classes):
         ref = pp.postprocess_cv2(det[i], logits[i, ..., 1:] if n_classes else None, scale=4, min_area_threshold=5)
         assert len(found[i]) == len(ref)
         for o, (b, c) in zip(found[i], ref):
-            assert pp.boxes_equivalent(o.bbox, b, tol=0) or pp.boxes_equivalent(o.bbox, b, tol=4)
+            assert pp.boxes_equivalent(o.bbox, b, tol=0) or pp.is_equal_area_tie(o.bbox, b)
             if n_classes:
                 assert o.object_type == c
     # float input = already preprocessed (Keras semantics): same result
@@ -92,7 +92,7 @@ def test_postprocess_and_contours_api(golden):
         assert len(objs) == len(boxes) == n
         for b, g in zip(boxes, fb[o:o + n]):
             assert b.dtype == np.float32 and b.shape == (8,)
-            assert pp.boxes_equivalent(np.round(b * 4), np.round(g * 4), tol=4)
+            assert pp.boxes_equivalent(np.round(b * 4), np.round(g * 4), tol=0)
         assert [int(c["area_x2"]) for c in cnts] == list(golden["m64x96_kept_area_x2"][o:o + n])
         o += n
 
