@@ -82,8 +82,10 @@ int ubd_get_weights(ubd_handle h, float* const* arrays, const int64_t* n_elems, 
 /* Tuning / diagnostic switches: "chunk" (images per sweep of the dilated layers, 0 = auto), "stem_chunk"
  * (images per stem launch, 0 = auto), "max_comps" (component slots per image), "max_points" (hull
  * candidate capacity), "precision" (UBD_FP32/TF32/BF16), "profile" (CUDA-event stage timers, see
- * ubd_get_stat), "dense_l2" (0: depthwise stem on the FP32 pipes), "tc_variant" (0: first-generation
- * tensor-core kernel for the dilated layers and the stem's L2), "tc_trace" (in-kernel cycle trace). */
+ * ubd_get_stat), "stem_variant" (grey input: 2 = fused image->L1->L2->L3 kernel, 1 = two-kernel stem, 0 = auto),
+ * "dense_l2" (0: depthwise stem on the FP32 pipes), "tc_variant" (0: first-generation tensor-core kernel for
+ * the dilated layers and the stem's L2), "tc_trace" (in-kernel cycle trace).  "max_comps" grows by itself when
+ * an image has more raw components than slots (the reference's cv2 path has no limit, utils.py:52). */
 int ubd_set_option(ubd_handle h, const char* name, int64_t value);
 
 /* ---- inference ------------------------------------------------------------------------------ */
@@ -121,6 +123,22 @@ int ubd_segment_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int
                     ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image);
 int ubd_forward_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int height, int width,
                     int preproc, float* d_logits);
+
+/* Pipelined form of ubd_segment (the loop of ModelRunner.run, model_runner.py:40-103, calls predict once per
+ * batch): submit queues one batch - host-to-device copy of the images, network, threshold, CC kernels, the
+ * copies of mask / logits back to mask_out / logits_out (nullable; must stay valid until the wait) - and returns a
+ * ticket; wait blocks until that batch is finished, computes its boxes on the host and fills comps_out
+ * (capacity max_comps >= the value given to submit) and n_comps_per_image.  At most two batches may be in flight
+ * and tickets are collected in submission order: the copy of batch k+1 and the host part of batch k then run under
+ * the kernels of the other batch.  Pass pinned host memory for the copies to be asynchronous.  The _dev form
+ * takes images already resident on the handle's device.  The synchronous entry points return UBD_ERR_STATE while
+ * a submitted batch is in flight. */
+int ubd_segment_submit(ubd_handle h, const void* images, int in_dtype, int n, int height, int width,
+                       int preproc, float logit_thr, int min_area_x2,
+                       uint8_t* mask_out, float* logits_out, int max_comps, int* ticket);
+int ubd_segment_submit_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int height, int width,
+                           int preproc, float logit_thr, int min_area_x2, int max_comps, int* ticket);
+int ubd_segment_wait(ubd_handle h, int ticket, ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image);
 
 /* Pure host helper, usable without a GPU: cv2.boxPoints(cv2.minAreaRect(pts)) for one point set
  * (utils.py:56-57).  pts: n_pts (x,y) int32 pairs (any superset of the hull); box: 8 floats. */

@@ -80,15 +80,21 @@ def test_degenerate_masks(eng):
     _check_against_spec(eng, m)
 
 
-def test_overflow_is_reported():
+def test_component_slots_grow_and_capacity_is_reported():
+    """The reference's cv2 path takes any number of contours (utils.py:52): the per-image slot table grows inside the
+    library and only the CC stage is redone; the caller's kept-component capacity is still an error."""
     from ubdvss_b200 import _lib
     from ubdvss_b200.engine import Engine
     e = Engine()
     e.set_option("max_comps", 4)
-    m = np.zeros((1, 32, 32), np.uint8); m[0, ::2, ::2] = 1      # 256 isolated pixels
+    m = np.zeros((2, 32, 32), np.uint8); m[0, ::2, ::2] = 1; m[1, 4:9, 4:9] = 1      # 256 isolated pixels | one block
+    _, comps, counts = e.postprocess(m, None, -1)
+    assert list(counts) == [256, 1]
+    labels, comps2 = pp.ccl_spec(m[0])
+    assert sorted(int(c["label"]) for c in comps[:256]) == sorted(int(c["label"]) for c in comps2)
     with pytest.raises(_lib.UbdError) as err:
-        e.postprocess(m, None, 0)
-    assert err.value.code == -4
+        e.postprocess(m, None, -1, max_comps=16)
+    assert err.value.code == -4 and "capacity" in str(err.value)
 
 
 def test_full_size_properties(eng):

@@ -155,3 +155,37 @@ def test_full_size_properties():
     perm = np.random.default_rng(0).permutation(64)
     mask_p, logits_p, _, comps_p, counts_p = eng.segment(np.ascontiguousarray(x[perm]), thr, 10, _lib.PREPROC_MOBILENET)
     assert np.array_equal(mask_p, mask[perm]) and np.array_equal(logits_p, logits[perm]) and np.array_equal(counts_p, counts[perm])
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_pipelined_submit_wait_equals_predict(precision):
+    """ubd_segment_submit / ubd_segment_wait (two batches in flight, ModelRunner.predict_stream) return exactly what
+    the synchronous ModelRunner.predict returns, batch by batch, for batches of different sizes and shapes."""
+    from ubdvss_b200 import _lib
+    from ubdvss_b200.model_runner import ModelRunner
+    from ubdvss_b200.net import B200Model
+    n_classes = 3
+    cfg = _cfg(n_classes)
+    w = onet.init_weights(n_classes, seed=77)
+    model = B200Model(cfg, weights=w, precision=precision)
+    runner = ModelRunner(cfg, pixel_threshold=0.45)
+    batches = [synth.synth_images(n, h, ww, seed=30 + i) for i, (n, h, ww) in
+               enumerate([(3, 128, 192), (5, 128, 192), (1, 256, 64), (4, 64, 64), (2, 192, 320)])]
+    want = [runner.predict(model, b, preprocessing="mobilenet_like") for b in batches]
+    got = list(runner.predict_stream(model, iter(batches), preprocessing="mobilenet_like"))
+    assert len(got) == len(want)
+    for (d0, c0, f0), (d1, c1, f1) in zip(want, got):
+        assert np.array_equal(d0, d1) and np.array_equal(c0, c1)
+        assert [[(tuple(o.bbox), getattr(o, "object_type", None)) for o in f] for f in f0] == \
+               [[(tuple(o.bbox), getattr(o, "object_type", None)) for o in f] for f in f1]
+    # call-order errors: a third submit, a synchronous call while batches are in flight, collecting out of order
+    t0 = model.segment_submit(batches[0], np.float32(0.0), 10, preprocessing="mobilenet_like")
+    t1 = model.segment_submit(batches[1], np.float32(0.0), 10, preprocessing="mobilenet_like")
+    for bad in (lambda: model.segment_submit(batches[2], np.float32(0.0), 10), lambda: runner.predict(model, batches[0]),
+                lambda: model.segment_wait(t1)):
+        with pytest.raises(_lib.UbdError) as err:
+            bad()
+        assert err.value.code in (-6,)
+    model.segment_wait(t0)
+    model.segment_wait(t1)
+    assert model.predict(batches[3]).shape == (4, 16, 16, 1 + n_classes)

@@ -51,6 +51,9 @@ SIGNATURES = {
     "ubd_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "ubd_segment_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp]),
     "ubd_forward_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ubd_segment_submit": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, C.POINTER(C.c_int)]),
+    "ubd_segment_submit_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, C.POINTER(C.c_int)]),
+    "ubd_segment_wait": (_i, [_vp, _i, _vp, _i, _vp]),
     "ubd_min_area_box": (_i, [_vp, _i, _vp]),
     "ubd_train_step": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ubd_train_step_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -117,6 +117,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return UBD_ERR_CUDA; }
   // preprocessing table for uint8 input: exactly what numpy computes, (v - 127.5) / 127.5 in
   // float64 (net.py:217-218 on a uint8 image) then cast to float32 at the Keras boundary
@@ -150,6 +151,12 @@ extern "C" int ubd_destroy(ubd_handle h) {
   if (h->h_stage) cudaFreeHost(h->h_stage);
   resolve_profile(h);
   for (cudaEvent_t ev : h->copy_events) cudaEventDestroy(ev);
+  for (ResultSlot& R : h->rs) {
+    if (R.h_hdr) cudaFreeHost(R.h_hdr);
+    if (R.ev_cc) cudaEventDestroy(R.ev_cc);
+    if (R.ev_fwd) cudaEventDestroy(R.ev_fwd);
+  }
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->own_stream);
   delete h;
@@ -468,9 +475,12 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
 // connected components on device mask -> host component list
 // ------------------------------------------------------------------------------------------------
 
-static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, int cls_stride, int n_cls,
-                      int n, int mh, int mw, int min_area_x2, int32_t* labels_out_host,
-                      ubd_component* comps_out, int max_out, int32_t* n_comps_per_image) {
+// Result slot s: everything the host reads back from one batch (kept counts, records, hull points) lives in the
+// slot's own buffers, so that the kernels of the next batch can run while the host finishes this one
+// (ubd_segment_submit / ubd_segment_wait); the per-pixel workspaces (parent, labels, ...) are shared.
+static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* d_cls, int cls_stride, int n_cls,
+                       int n, int mh, int mw, int min_area_x2, int max_out, int32_t* labels_out_host) {
+  ResultSlot& R = h->rs[s];
   const size_t npx = (size_t)mh * mw;
   const size_t pstride = (npx + 1 + 31) & ~(size_t)31;
   const int max_comps = h->opt_max_comps;
@@ -481,11 +491,21 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
   ENSURE(h->slot_of, (size_t)n * npx * sizeof(int));
   ENSURE(h->comps, (size_t)n * max_comps * sizeof(CompRec));
   ENSURE(h->cls_sums, (size_t)n * max_comps * std::max(n_cls, 1) * sizeof(unsigned long long));
-  ENSURE(h->n_comps, (size_t)(2 * n) * sizeof(int) + sizeof(CclTotals));
-  ENSURE(h->out_recs, (size_t)std::max(max_out, 1) * sizeof(OutRec));
   ENSURE(h->out_index, (size_t)n * max_comps * sizeof(int));
-  ENSURE(h->hull_pts, (size_t)max_pts * sizeof(HullPt));
-  int* d_ncomps = (int*)h->n_comps.p;
+  ENSURE(R.hdr, (size_t)(2 * n) * sizeof(int) + sizeof(CclTotals));
+  ENSURE(R.out_recs, (size_t)std::max(max_out, 1) * sizeof(OutRec));
+  ENSURE(R.hull_pts, (size_t)max_pts * sizeof(HullPt));
+  const size_t hdr_ints = n + sizeof(CclTotals) / sizeof(int);
+  if (R.h_hdr_cap < hdr_ints) {
+    if (R.h_hdr) cudaFreeHost(R.h_hdr);
+    R.h_hdr = nullptr; R.h_hdr_cap = 0;
+    UBD_CUDA(cudaMallocHost(&R.h_hdr, (hdr_ints + 64) * sizeof(int)));
+    R.h_hdr_cap = hdr_ints + 64;
+  }
+  if (!R.ev_cc) UBD_CUDA(cudaEventCreateWithFlags(&R.ev_cc, cudaEventDisableTiming));
+  R.n = n; R.mh = mh; R.mw = mw; R.max_pts = max_pts; R.max_comps_img = max_comps; R.max_out = max_out;
+  R.d_mask_used = d_mask; R.d_cls_used = d_cls; R.cls_stride = cls_stride; R.n_cls = n_cls; R.min_area_x2 = min_area_x2;
+  int* d_ncomps = (int*)R.hdr.p;
   int* d_kept = d_ncomps + n;
   CclTotals* d_tot = (CclTotals*)(d_kept + n);
   int* parent = (int*)h->parent.p;
@@ -496,66 +516,85 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
 
   dim3 tgrid((mw + 31) / 32, (mh + 7) / 8, n), tblock(256);
   dim3 lgrid((unsigned)((npx + 1 + 255) / 256), n);
-  HostTimer* ht_enq = new HostTimer(h, 1);
-  ProfScope* ps_ccl = new ProfScope(h, &h->prof_ccl);
-  UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
-  dim3 lgrid32((mw + CCL_T - 1) / CCL_T, (mh + CCL_T - 1) / CCL_T, n);
-  ccl_local_kernel<<<lgrid32, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
-  const int n_border = ((mh - 1) / CCL_T) * mw + ((mw - 1) / CCL_T) * 2 * mh;
-  if (n_border > 0) {
-    dim3 bgrid2((unsigned)((n_border + 255) / 256), n);
-    ccl_border_kernel<<<bgrid2, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+  {
+    HostTimer ht_enq(h, 1);
+    ProfScope ps_ccl(h, &h->prof_ccl);
+    UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
+    dim3 lgrid32((mw + CCL_T - 1) / CCL_T, (mh + CCL_T - 1) / CCL_T, n);
+    ccl_local_kernel<<<lgrid32, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+    const int n_border = ((mh - 1) / CCL_T) * mw + ((mw - 1) / CCL_T) * 2 * mh;
+    if (n_border > 0) {
+      dim3 bgrid2((unsigned)((n_border + 255) / 256), n);
+      ccl_border_kernel<<<bgrid2, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+    }
+    uint8_t* outer = (uint8_t*)h->outer.p;
+    ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+    dim3 bgrid((unsigned)((2 * (mh + mw) + 255) / 256), n);
+    ccl_mark_outer_kernel<<<bgrid, 256, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+    ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+    ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, outer, labels, mh, mw, pstride); LAUNCH_CHECK();
+    ccl_slots_kernel<<<n, 1024, 0, h->stream>>>(labels, slot_of, comps, cls_sums, n_cls, d_ncomps, mh, mw, max_comps); LAUNCH_CHECK();
+    dim3 sgrid((mw + 1 + 31) / 32, (mh + 1 + 7) / 8, n);
+    ccl_stats_kernel<<<sgrid, tblock, 0, h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls, mh, mw, max_comps); LAUNCH_CHECK();
+    ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
+    ccl_compact_kernel<<<n, 256, 0, h->stream>>>(comps, cls_sums, n_cls, d_ncomps, d_kept, (OutRec*)R.out_recs.p,
+                                                 (int*)h->out_index.p, max_comps, max_out, min_area_x2); LAUNCH_CHECK();
+    ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)R.hull_pts.p,
+                                                       d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();
   }
-  uint8_t* outer = (uint8_t*)h->outer.p;
-  ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, outer, mh, mw, pstride); LAUNCH_CHECK();
-  dim3 bgrid((unsigned)((2 * (mh + mw) + 255) / 256), n);
-  ccl_mark_outer_kernel<<<bgrid, 256, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, outer, labels, mh, mw, pstride); LAUNCH_CHECK();
-  ccl_slots_kernel<<<n, 1024, 0, h->stream>>>(labels, slot_of, comps, cls_sums, n_cls, d_ncomps, mh, mw, max_comps); LAUNCH_CHECK();
-  dim3 sgrid((mw + 1 + 31) / 32, (mh + 1 + 7) / 8, n);
-  ccl_stats_kernel<<<sgrid, tblock, 0, h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls, mh, mw, max_comps); LAUNCH_CHECK();
-  ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
-  ccl_compact_kernel<<<n, 256, 0, h->stream>>>(comps, cls_sums, n_cls, d_ncomps, d_kept, (OutRec*)h->out_recs.p,
-                                               (int*)h->out_index.p, max_comps, max_out, min_area_x2); LAUNCH_CHECK();
-  ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)h->hull_pts.p,
-                                                     d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();
-  delete ps_ccl;
-  delete ht_enq;
-  HostTimer* ht_s1 = new HostTimer(h, 2);
-
-  // header: kept counts per image + totals (one small D2H), then the records and hull points
-  std::vector<int> header(n + sizeof(CclTotals) / sizeof(int));
-  UBD_CUDA(cudaMemcpyAsync(header.data(), d_kept, header.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  // header: kept counts per image + totals (one small D2H into pinned memory); the records and hull points follow
+  // in ccl_finish once their sizes are known
+  UBD_CUDA(cudaMemcpyAsync(R.h_hdr, d_kept, hdr_ints * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (labels_out_host)
     UBD_CUDA(cudaMemcpyAsync(labels_out_host, labels, (size_t)n * npx * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  UBD_CUDA(cudaStreamSynchronize(h->stream));
-  delete ht_s1;
+  UBD_CUDA(cudaEventRecord(R.ev_cc, h->stream));
+  return UBD_OK;
+}
+
+static constexpr int kCclRetry = 1;     // ccl_finish: an image had more raw components than slots; opt_max_comps was raised
+
+static int ccl_finish(ubd_handle h, int s, ubd_component* comps_out, int max_out, int32_t* n_comps_per_image) {
+  ResultSlot& R = h->rs[s];
+  const int n = R.n;
+  {
+    HostTimer ht_s1(h, 2);
+    UBD_CUDA(cudaEventSynchronize(R.ev_cc));
+  }
   CclTotals tot;
-  memcpy(&tot, header.data() + n, sizeof(tot));
-  if (tot.max_ncomp > max_comps)
-    UBD_FAIL(UBD_ERR_OVERFLOW, "an image has " + std::to_string(tot.max_ncomp) + " components > max_comps option " +
-                                   std::to_string(max_comps) + " (ubd_set_option \"max_comps\")");
+  memcpy(&tot, R.h_hdr + n, sizeof(tot));
+  if (tot.max_ncomp > R.max_comps_img) {
+    // the reference's cv2 path takes any number of contours (utils.py:52): grow the slot table and redo the CC stage only
+    int want = R.max_comps_img;
+    while (want < tot.max_ncomp) want *= 2;
+    h->opt_max_comps = want;
+    return kCclRetry;
+  }
   if (tot.total_kept > max_out)
     UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_kept) + " kept components exceed the caller's capacity " + std::to_string(max_out));
-  if (tot.total_pts > max_pts)
-    UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_pts) + " hull candidate points exceed max_points " + std::to_string(max_pts));
-  for (int i = 0; i < n; ++i) n_comps_per_image[i] = header[i];
+  if (tot.total_pts > R.max_pts)
+    UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_pts) + " hull candidate points exceed max_points " + std::to_string(R.max_pts));
+  for (int i = 0; i < n; ++i) n_comps_per_image[i] = R.h_hdr[i];
   if (tot.total_kept == 0) return UBD_OK;
-  HostTimer* ht_s2 = new HostTimer(h, 3);
-  std::vector<OutRec> recs(tot.total_kept);
-  std::vector<HullPt> pts(tot.total_pts);
-  UBD_CUDA(cudaMemcpyAsync(recs.data(), h->out_recs.p, recs.size() * sizeof(OutRec), cudaMemcpyDeviceToHost, h->stream));
-  if (!pts.empty())
-    UBD_CUDA(cudaMemcpyAsync(pts.data(), h->hull_pts.p, pts.size() * sizeof(HullPt), cudaMemcpyDeviceToHost, h->stream));
-  UBD_CUDA(cudaStreamSynchronize(h->stream));
-  delete ht_s2;
+  std::vector<OutRec>& recs = R.recs;
+  std::vector<HullPt>& pts = R.pts;
+  {
+    HostTimer ht_s2(h, 3);
+    recs.resize(tot.total_kept);
+    pts.resize(tot.total_pts);
+    // on the read-back stream: the handle's own stream may already hold the next batch's kernels
+    UBD_CUDA(cudaMemcpyAsync(recs.data(), R.out_recs.p, recs.size() * sizeof(OutRec), cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (!pts.empty())
+      UBD_CUDA(cudaMemcpyAsync(pts.data(), R.hull_pts.p, pts.size() * sizeof(HullPt), cudaMemcpyDeviceToHost, h->d2h_stream));
+    UBD_CUDA(cudaStreamSynchronize(h->d2h_stream));
+  }
   HostTimer ht_host(h, 4);
   // Reduce the hull candidates to the leftmost / rightmost one per (component, row) -- only those can
   // be hull vertices -- then the min-area box of each component on the host.
-  std::vector<int> row0(tot.total_kept + 1, 0);
+  std::vector<int>& row0 = R.row0;
+  std::vector<int>& ext = R.ext;
+  row0.assign(tot.total_kept + 1, 0);
   for (int i = 0; i < tot.total_kept; ++i) row0[i + 1] = row0[i] + (recs[i].ymax - recs[i].ymin + 1);
-  std::vector<int> ext(2 * (size_t)row0[tot.total_kept]);
+  ext.resize(2 * (size_t)row0[tot.total_kept]);
   for (size_t k = 0; k < ext.size(); k += 2) { ext[k] = 0x7fffffff; ext[k + 1] = -1; }
   for (const HullPt& p : pts) {
     const int x = p.xy & 0xffff, y = p.xy >> 16;
@@ -563,7 +602,7 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
     if (x < e[0]) e[0] = x;
     if (x > e[1]) e[1] = x;
   }
-  std::vector<int32_t> xy;
+  std::vector<int32_t>& xy = R.xy;
   for (int i = 0; i < tot.total_kept; ++i) {
     const OutRec& r = recs[i];
     ubd_component& c = comps_out[i];
@@ -579,6 +618,19 @@ static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, i
     ubd_min_area_box(xy.data(), (int)(xy.size() / 2), c.box);
   }
   return UBD_OK;
+}
+
+// CC stage of a batch, synchronously (slot 0); retried with a larger slot table when an image overflows it.
+static int ccl_device(ubd_handle h, const uint8_t* d_mask, const float* d_cls, int cls_stride, int n_cls,
+                      int n, int mh, int mw, int min_area_x2, int32_t* labels_out_host,
+                      ubd_component* comps_out, int max_out, int32_t* n_comps_per_image) {
+  if (h->rs[0].busy || h->rs[1].busy) UBD_FAIL(UBD_ERR_STATE, "a submitted batch is still in flight (ubd_segment_wait)");
+  for (;;) {
+    int rc = ccl_enqueue(h, 0, d_mask, d_cls, cls_stride, n_cls, n, mh, mw, min_area_x2, max_out, labels_out_host);
+    if (rc) return rc;
+    rc = ccl_finish(h, 0, comps_out, max_out, n_comps_per_image);
+    if (rc != kCclRetry) return rc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -672,6 +724,83 @@ extern "C" int ubd_segment(ubd_handle h, const void* images, int in_dtype, int n
   if (rc) return rc;
   if (mask_out || logits_out) UBD_CUDA(cudaStreamSynchronize(h->copy_stream));
   return h->precision == UBD_FP32 ? UBD_OK : tc_check_error(h);
+}
+
+// ---- pipelined form of ubd_segment / ubd_segment_dev -------------------------------------------------------------
+// submit enqueues everything of one batch (H2D of the images on the copy stream, network, threshold, CC kernels, the
+// D2H of mask / logits on the read-back stream) and returns; wait blocks until that batch is done and finishes its
+// boxes on the host.  With two batches in flight the H2D copy of batch k+1 and the host tail of batch k run under
+// the kernels of the other batch.
+static int segment_submit_common(ubd_handle h, const void* images, bool on_device, int in_dtype, int n, int H, int W, int preproc,
+                                 float logit_thr, int min_area_x2, uint8_t* mask_out, float* logits_out, int max_comps, int* ticket) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_image_args(h, images, in_dtype, n, H, W, preproc);
+  if (rc) return rc;
+  if (!ticket || max_comps < 0) UBD_FAIL(UBD_ERR_ARG, "ticket is NULL or max_comps < 0");
+  UBD_CUDA(cudaSetDevice(h->device));
+  const int s = (int)(h->next_ticket & 1);
+  ResultSlot& R = h->rs[s];
+  if (R.busy) UBD_FAIL(UBD_ERR_STATE, "two batches are already in flight: call ubd_segment_wait first");
+  const size_t ib = image_bytes(h, in_dtype, n, H, W);
+  const size_t q = (size_t)n * (H / 4) * (W / 4);
+  const void* d_img = images;
+  if (!on_device) { ENSURE(R.d_images, ib); d_img = R.d_images.p; }
+  ENSURE(R.d_mask, q);
+  ENSURE(R.d_logits, q * h->spec.n_out * sizeof(float));
+  rc = forward_device(h, d_img, in_dtype, n, H, W, preproc, (float*)R.d_logits.p, (uint8_t*)R.d_mask.p, logit_thr,
+                      on_device ? nullptr : images);
+  if (rc) return rc;
+  if (mask_out || logits_out) {
+    if (!R.ev_fwd) UBD_CUDA(cudaEventCreateWithFlags(&R.ev_fwd, cudaEventDisableTiming));
+    UBD_CUDA(cudaEventRecord(R.ev_fwd, h->stream));
+    UBD_CUDA(cudaStreamWaitEvent(h->d2h_stream, R.ev_fwd, 0));
+    if (mask_out) UBD_CUDA(cudaMemcpyAsync(mask_out, R.d_mask.p, q, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (logits_out) UBD_CUDA(cudaMemcpyAsync(logits_out, R.d_logits.p, q * h->spec.n_out * sizeof(float), cudaMemcpyDeviceToHost, h->d2h_stream));
+  }
+  const int n_cls = h->n_classes;
+  rc = ccl_enqueue(h, s, (uint8_t*)R.d_mask.p, n_cls ? (float*)R.d_logits.p + 1 : nullptr, h->spec.n_out, n_cls, n, H / 4, W / 4,
+                   min_area_x2, max_comps, nullptr);
+  if (rc) return rc;
+  R.busy = true;
+  R.ticket = h->next_ticket++;
+  *ticket = (int)(R.ticket & 0x7fffffff);
+  return UBD_OK;
+}
+
+extern "C" int ubd_segment_submit(ubd_handle h, const void* images, int in_dtype, int n, int H, int W, int preproc,
+                                  float logit_thr, int min_area_x2, uint8_t* mask_out, float* logits_out, int max_comps, int* ticket) {
+  return segment_submit_common(h, images, false, in_dtype, n, H, W, preproc, logit_thr, min_area_x2, mask_out, logits_out, max_comps, ticket);
+}
+
+extern "C" int ubd_segment_submit_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int H, int W, int preproc,
+                                      float logit_thr, int min_area_x2, int max_comps, int* ticket) {
+  return segment_submit_common(h, d_images, true, in_dtype, n, H, W, preproc, logit_thr, min_area_x2, nullptr, nullptr, max_comps, ticket);
+}
+
+extern "C" int ubd_segment_wait(ubd_handle h, int ticket, ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image) {
+  if (!h) return UBD_ERR_ARG;
+  if (!comps_out || !n_comps_per_image) UBD_FAIL(UBD_ERR_ARG, "component outputs are NULL");
+  UBD_CUDA(cudaSetDevice(h->device));
+  int s = -1;
+  for (int i = 0; i < 2; ++i)
+    if (h->rs[i].busy && (int)(h->rs[i].ticket & 0x7fffffff) == ticket) s = i;
+  if (s < 0) UBD_FAIL(UBD_ERR_STATE, "unknown ticket");
+  ResultSlot& R = h->rs[s];
+  // tickets complete in submission order: the older batch must be collected first
+  if (h->rs[s ^ 1].busy && h->rs[s ^ 1].ticket < R.ticket) UBD_FAIL(UBD_ERR_STATE, "an older batch has not been collected yet");
+  if (max_comps < R.max_out) UBD_FAIL(UBD_ERR_ARG, "comps_out is smaller than the capacity given to ubd_segment_submit");
+  int rc;
+  for (;;) {
+    rc = ccl_finish(h, s, comps_out, R.max_out, n_comps_per_image);
+    if (rc != kCclRetry) break;
+    // rare: more raw components in an image than slots; redo the CC stage of this batch behind whatever is queued
+    rc = ccl_enqueue(h, s, R.d_mask_used, R.d_cls_used, R.cls_stride, R.n_cls, R.n, R.mh, R.mw, R.min_area_x2, R.max_out, nullptr);
+    if (rc) break;
+  }
+  R.busy = false;
+  if (rc) return rc;
+  UBD_CUDA(cudaStreamSynchronize(h->d2h_stream));        // mask / logits of this batch have landed
+  return h->precision == UBD_FP32 ? UBD_OK : tc_check_error_on(h, h->d2h_stream);
 }
 
 extern "C" int ubd_postprocess(ubd_handle h, const uint8_t* mask, const float* cls_logits, int n, int mh, int mw,

@@ -391,10 +391,6 @@ ccl_stats_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label
 
 // Kept components (2*contourArea > min_area_x2, utils.py:55), compacted image-major and, inside an
 // image, in DESCENDING label order (cv2 lists external contours bottom-up).
-struct OutRec {
-  int image, label, xmin, ymin, xmax, ymax, n_pixels, n_filled, area_x2, class_id, slot;
-};
-struct CclTotals { int total_kept, total_pts, max_ncomp, pad; };
 
 __global__ void __launch_bounds__(256)
 ccl_count_kept_kernel(const CompRec* __restrict__ comps, const int* __restrict__ n_comps,
@@ -485,7 +481,6 @@ ccl_compact_kernel(const CompRec* __restrict__ comps, const unsigned long long* 
 // over its pixels for some direction u, so its neighbour in the x-direction of u and its neighbour
 // in the y-direction of u are both outside the component: only such corner pixels are emitted
 // (a superset of the hull vertices, all that cv2.minAreaRect needs, utils.py:56).
-struct HullPt { int comp; int xy; };     // comp = index into the compacted output; xy = (y << 16) | x
 __global__ void __launch_bounds__(256)
 ccl_points_kernel(const int* __restrict__ labels, const int* __restrict__ slot_of,
                   const int* __restrict__ out_index_of_slot, HullPt* __restrict__ pts,

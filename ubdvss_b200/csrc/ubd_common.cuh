@@ -51,6 +51,13 @@ static inline WeightSpec make_weight_spec(int grey, int n_classes) {
   return s;
 }
 
+// Results of the connected-component stage as the host reads them back (ubd_ccl.cuh writes them).
+struct OutRec {
+  int image, label, xmin, ymin, xmax, ymax, n_pixels, n_filled, area_x2, class_id, slot;
+};
+struct CclTotals { int total_kept, total_pts, max_ncomp, pad; };
+struct HullPt { int comp; int xy; };     // comp = index into the compacted output; xy = (y << 16) | x
+
 #define UBD_CUDA(call)                                                                      \
   do {                                                                                      \
     cudaError_t e_ = (call);                                                                \

@@ -5,6 +5,22 @@
 
 struct DevBuf { void* p = nullptr; size_t cap = 0; };
 
+// Host-visible results of one batch (see ccl_enqueue / ccl_finish in ubd_api.cu): two slots so that a submitted batch
+// can be finished on the host while the next one runs.
+struct ResultSlot {
+  DevBuf hdr, out_recs, hull_pts;          // device: raw / kept counts + totals, kept records, hull candidates
+  DevBuf d_images, d_mask, d_logits;       // device: staging of a submitted batch and its outputs
+  int* h_hdr = nullptr; size_t h_hdr_cap = 0;     // pinned copy of hdr (kept counts + totals)
+  cudaEvent_t ev_cc = nullptr, ev_fwd = nullptr;
+  int n = 0, mh = 0, mw = 0, max_pts = 0, max_comps_img = 0, max_out = 0;
+  const uint8_t* d_mask_used = nullptr; const float* d_cls_used = nullptr;
+  int cls_stride = 0, n_cls = 0, min_area_x2 = 0;
+  bool busy = false;
+  long long ticket = 0;
+  std::vector<OutRec> recs; std::vector<HullPt> pts;      // host scratch, reused
+  std::vector<int> row0, ext; std::vector<int32_t> xy;
+};
+
 struct ubd_handle_s {
   int device = 0;
   bool grey = true, fml = true;
@@ -15,6 +31,9 @@ struct ubd_handle_s {
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;      // H2D of chunk k+1 overlaps the compute of chunk k
+  cudaStream_t d2h_stream = nullptr;       // read-back of results while the next batch computes
+  ResultSlot rs[2];
+  long long next_ticket = 0;
   std::vector<cudaEvent_t> copy_events;
   // optional CUDA-event profiling of kernel groups (option "profile")
   bool profile = false;
@@ -46,7 +65,7 @@ struct ubd_handle_s {
   int map_h = 0, map_w = 0, map_n = 0, map_prec = -1;
   long long act2_tag = 0;                  // geometry the parity-split act2 buffer was last zeroed for     // shape the padded maps were last zeroed for
   DevBuf outer;
-  DevBuf parent, labels, slot_of, comps, cls_sums, n_comps, out_recs, out_index, hull_pts;
+  DevBuf parent, labels, slot_of, comps, cls_sums, out_index;
   DevBuf l2dense;                 // merged dense 3x3 kernel of the stem's L2 (+ bias)
   DevBuf stem_wimg;               // pointwise B images of L2 / L3 for the tensor-core stem
   bool stem_weights_dirty = true;
@@ -65,7 +84,8 @@ struct ubd_handle_s {
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &n_comps, &out_recs, &out_index, &hull_pts, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
+            &cls_sums, &out_index, &rs[0].hdr, &rs[0].out_recs, &rs[0].hull_pts, &rs[0].d_images, &rs[0].d_mask, &rs[0].d_logits,
+            &rs[1].hdr, &rs[1].out_recs, &rs[1].hull_pts, &rs[1].d_images, &rs[1].d_mask, &rs[1].d_logits, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
   }
 };

@@ -643,14 +643,15 @@ static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer,
   return UBD_OK;
 }
 
-// Reads (and clears) the device-side barrier-timeout flag; call after a stream synchronize.
-static int tc_check_error(ubd_handle h) {
+// Reads (and clears) the device-side barrier-timeout flag; call after a stream synchronize.  `on` = the stream the
+// read is queued on: the handle's own, or the read-back stream when the next batch is already queued on the former.
+static int tc_check_error_on(ubd_handle h, cudaStream_t on) {
   if (!h->tc_weights.p) return UBD_OK;
   int codes[16] = {0};
-  UBD_CUDA(cudaMemcpyAsync(codes, tc_err_flag(h), sizeof(codes), cudaMemcpyDeviceToHost, h->stream));
-  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  UBD_CUDA(cudaMemcpyAsync(codes, tc_err_flag(h), sizeof(codes), cudaMemcpyDeviceToHost, on));
+  UBD_CUDA(cudaStreamSynchronize(on));
   if (codes[0]) {
-    cudaMemsetAsync(tc_err_flag(h), 0, sizeof(codes), h->stream);
+    cudaMemsetAsync(tc_err_flag(h), 0, sizeof(codes), on);
     std::string where;
     for (int i = 1; i < 16; ++i)
       if (codes[i]) where += " w" + std::to_string(i - 1) + ":" + std::to_string(codes[i] >> 24) + "/" + std::to_string(codes[i] & 0xFFFFFF);
@@ -658,3 +659,4 @@ static int tc_check_error(ubd_handle h) {
   }
   return UBD_OK;
 }
+static int tc_check_error(ubd_handle h) { return tc_check_error_on(h, h->stream); }

@@ -240,6 +240,38 @@ class Engine:
                                                  C.c_void_p(d_logits_ptr or 0), ptr(comps), cap, ptr(counts)))
         return comps[:int(counts.sum())], counts
 
+    # ---------------------------------------------------------------- pipelined inference (two batches in flight)
+    def segment_submit(self, images, logit_thr: float, min_area_x2: int, preproc: int = _lib.PREPROC_NONE,
+                       mask_out=None, logits_out=None, max_comps: int = 0, device_ptr: int = 0, shape=None, dtype=None):
+        """Queue one batch and return a ticket object for ``segment_wait``.  ``images``: host array (pass pinned memory
+        for an asynchronous copy), or ``device_ptr`` + ``shape`` (n, H, W) + ``dtype`` for device-resident input.
+        ``mask_out`` / ``logits_out``: optional host arrays filled by the time ``segment_wait`` returns."""
+        if device_ptr:
+            n, H, W = shape
+            dt = dtype
+            x = None
+        else:
+            x, dt = self._images(images)
+            n, H, W, _ = x.shape
+        cap = max_comps or max(1024, 64 * n)
+        t = C.c_int()
+        if device_ptr:
+            check(self._h, self._lib.ubd_segment_submit_dev(self._h, C.c_void_p(device_ptr), dt, n, H, W, preproc, np.float32(logit_thr),
+                                                            int(min_area_x2), cap, C.byref(t)))
+        else:
+            check(self._h, self._lib.ubd_segment_submit(self._h, ptr(x), dt, n, H, W, preproc, np.float32(logit_thr), int(min_area_x2),
+                                                        ptr(mask_out), ptr(logits_out), cap, C.byref(t)))
+        # the ticket keeps the host buffers alive until the batch has been collected
+        return {"ticket": t.value, "n": n, "cap": cap, "keep": (x, mask_out, logits_out)}
+
+    def segment_wait(self, ticket):
+        """-> (comps, counts) of a submitted batch (tickets are collected in submission order)."""
+        comps = np.zeros(ticket["cap"], COMPONENT_DTYPE)
+        counts = np.zeros(ticket["n"], np.int32)
+        check(self._h, self._lib.ubd_segment_wait(self._h, ticket["ticket"], ptr(comps), ticket["cap"], ptr(counts)))
+        ticket["keep"] = None
+        return comps[:int(counts.sum())], counts
+
     def launch_count(self) -> int:
         return int(self._lib.ubd_launch_count(self._h))
 

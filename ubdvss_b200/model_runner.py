@@ -46,6 +46,38 @@ class ModelRunner:
             found_objects = self.rescale(found_objects, meta_infos)
         return detection, classification_logits, found_objects
 
+    def predict_stream(self, model, batches, rescale=False, preprocessing=None):
+        """The per-batch loop of ``ModelRunner.run`` (model_runner.py:40-103: ``next(generator)`` -> ``predict`` ->
+        consume) with two batches in flight: while batch k runs on the GPU, batch k+1 is being copied and batch
+        k-1's boxes are finished on the host.  ``batches`` yields ``images`` or ``(images, meta_infos)``; yields
+        exactly what ``predict`` returns for each batch, in order, with identical values."""
+        cfg = self._net_config
+        classification = cfg.is_classification_supported()
+        scale = cfg.get_scale()
+        ma2 = min_area_x2(cfg.get_min_pixels_for_detection())
+        thr32 = np.float32(self._logit_threshold)
+
+        def finish(entry):
+            ticket, metas = entry
+            mask, logits, comps, counts = model.segment_wait(ticket)
+            found, o = [], 0
+            for c in counts:
+                found.append(markups_from_components(comps[o:o + c], scale, classification))
+                o += c
+            if rescale:
+                found = self.rescale(found, metas)
+            return mask[..., None].astype(np.int64), logits[..., 1:], found
+
+        pending = []
+        for item in batches:
+            images, metas = item if isinstance(item, tuple) else (item, None)
+            assert not rescale or (metas is not None and len(images) == len(metas))
+            pending.append((model.segment_submit(images, thr32, ma2, preprocessing=preprocessing), metas))
+            if len(pending) == 2:
+                yield finish(pending.pop(0))
+        while pending:
+            yield finish(pending.pop(0))
+
     @staticmethod
     def rescale(found_objects, meta_infos):
         """model_runner.py:140-148."""

@@ -210,6 +210,20 @@ class B200Model:
             return mask, logits, comps, counts, labels
         return mask, logits, comps, counts
 
+    def segment_submit(self, images, logit_thr, min_area_x2, preprocessing=None):
+        """Queue one batch (two may be in flight); see ``ModelRunner.predict_stream``."""
+        x = np.asarray(images)
+        n, H, W = x.shape[:3]
+        mask = np.empty((n, H // 4, W // 4), np.uint8)
+        logits = np.empty((n, H // 4, W // 4, 1 + self.n_classes), np.float32)
+        t = self._engine.segment_submit(x, logit_thr, min_area_x2, _PREPROC_CODE[preprocessing], mask_out=mask, logits_out=logits)
+        t["mask"], t["logits"] = mask, logits
+        return t
+
+    def segment_wait(self, ticket):
+        comps, counts = self._engine.segment_wait(ticket)
+        return ticket["mask"], ticket["logits"], comps, counts
+
     # ---- weights (net.py:418-427)
     def get_weights(self):
         return self._engine.get_weights()
