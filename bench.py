@@ -7,7 +7,8 @@ one batch of synthetic 1024x1024 grayscale images per GPU (BASELINE configs[1]: 
             max over ranks, whole-job images/sec
   e2e       same metric through the reference-facing C-ABI call (ubd_segment) with pinned HOST
             buffers: H2D of the images and D2H of mask + components inside the timed region
-  roofline  the dominant kernel (dilated 3x3 conv) vs the measured bf16 tensor peak (tf32 = 1/2)
+  roofline  the dominant kernel (dilated 3x3 conv): algorithmic FLOP / launch time vs the measured bf16 tensor
+            peak (tf32 = 1/2); stem, CC and whole-step fractions beside it
   cpu_baseline  the CPU oracle (torch-CPU restatement of the reference + its cv2 calls) on a bounded
             sample, rank 0, N=1 only
 `--impl reference` times that CPU restatement as the reference arm (TF/Keras cannot run here).
@@ -149,32 +150,32 @@ class ClockSampler:
                 "power_w_max": pmax, "source": "nvidia-smi"}
 
 
-def make_images(batch, size, seed=1):
-    """`batch` uint8 images of size x size: 8 distinct synthetic images, tiled (synthetic data)."""
+def make_images(batch, h, w, seed=1):
+    """`batch` uint8 images of h x w: 8 distinct synthetic images, tiled (synthetic data)."""
     from ubdvss_b200 import synth
-    base = synth.synth_images(min(batch, 8), size, size, seed=seed)
+    base = synth.synth_images(min(batch, 8), h, w, seed=seed)
     reps = -(-batch // base.shape[0])
     return np.ascontiguousarray(np.concatenate([base] * reps, 0)[:batch])
 
 
-def cpu_reference_step(weights, images_u8, thr):
+def cpu_reference_step(weights, images_u8, thr, n_classes):
     """One pass of the CPU restatement of the reference over `images_u8` (oracle, test infra)."""
     from oracle import net as onet, postproc as pp
     x = onet.preprocess(images_u8.astype(np.float64), "mobilenet_like").astype(np.float32)
     logits = onet.forward_torch(weights, x)
     det = pp.threshold_mask(logits[..., :1], thr)
-    return [pp.postprocess_cv2(det[i], None, 4, 5) for i in range(det.shape[0])]
+    return [pp.postprocess_cv2(det[i], logits[i, ..., 1:] if n_classes else None, 4, 5) for i in range(det.shape[0])]
 
 
-def time_cpu(weights, images_u8, thr, steps, warmup):
+def time_cpu(weights, images_u8, thr, n_classes, steps, warmup):
     import torch
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     for _ in range(warmup):
-        cpu_reference_step(weights, images_u8, thr)
+        cpu_reference_step(weights, images_u8, thr, n_classes)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(weights, images_u8, thr)
+        cpu_reference_step(weights, images_u8, thr, n_classes)
     dt = time.perf_counter() - t0
     return images_u8.shape[0] * steps / dt, dt / steps, cores
 
@@ -202,20 +203,34 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+# BASELINE.json configs -> (batch per GPU, H, W, precision, classes).  C: 3840x2160 scans are fed as 2176x3840
+# (sides rounded up to multiples of 64, segmap_manager.py:153-165); D: 256 images over 8 GPUs = 32 per GPU.
+CONFIGS = {
+    "B": dict(idx=1, batch=64, h=1024, w=1024, precision="tf32", n_classes=0,
+              text="batch-64 synthetic 1024x1024 grayscale inference per GPU, fp32/TF32, threshold + CC boxes"),
+    "C": dict(idx=2, batch=8, h=2176, w=3840, precision="tf32", n_classes=0,
+              text="batch-sharded 3840x2160 document scans (network input 2176x3840), 8 per GPU, threshold + CC boxes"),
+    "D": dict(idx=3, batch=32, h=1024, w=1024, precision="bf16", n_classes=26,
+              text="bf16 inference with the 26-type barcode head (detection map + per-pixel class vote), batch 256 over 8 GPUs = 32 per GPU, 1024x1024"),
+}
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE configs[1])")
-    ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"],
-                    help="configs[1] is quoted as fp32/TF32: tf32 tensor-core path by default")
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="BASELINE.json configs[1] (default), [2] or [3]")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--size", type=int, default=0, help="square image side (default: the config's shape)")
+    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", ""), choices=["", "fp32", "tf32", "bf16"],
+                    help="default: the config's (configs[1] is quoted as fp32/TF32: tf32 tensor-core path)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-E training-step measurement")
+    ap.add_argument("--sync-api", action="store_true", help="time the synchronous ubd_segment[_dev] calls instead of submit/wait")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,27 +238,36 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from ubdvss_b200 import synth as usynth
 
-    weights = usynth.synth_weights(0, seed=1234)               # random init of the architecture (no oracle on this arm)
-    cfg = {"workload": f"configs[1]: batch-{args.batch} synthetic {args.size}x{args.size} grayscale inference per GPU, "
-                       f"{args.precision}, threshold + CC boxes", "batch_per_gpu": args.batch, "image": [args.size, args.size, 1],
-           "input_dtype": "uint8 (mobilenet_like preprocessing folded into L1)", "precision": args.precision,
+    C = CONFIGS[args.config]
+    B = args.batch or C["batch"]
+    H, W = (args.size, args.size) if args.size else (C["h"], C["w"])
+    precision = args.precision or C["precision"]
+    n_classes = C["n_classes"]
+    # random init of the architecture, scaled layer by layer so that the logit map follows the image content
+    weights = usynth.synth_weights(n_classes, seed=1234, calibrated=True)
+    thr = 0.0                                                  # pixel_threshold 0.5 (model_runner.py:37-38)
+    cfg = {"workload": f"configs[{C['idx']}]: {C['text']}" + ("" if (B, H, W, precision) == (C["batch"], C["h"], C["w"], C["precision"])
+                                                              else f" [overridden: batch {B}, {H}x{W}, {precision}]"),
+           "batch_per_gpu": B, "image": [H, W, 1], "n_classes": n_classes,
+           "input_dtype": "uint8 (mobilenet_like preprocessing folded into L1)", "precision": precision,
+           "weights": "random init (Glorot) + layer-sequential unit-variance scaling; pixel_threshold 0.5, min_area 5",
            "parallelism": f"batch-sharded x{world}, no collective",
-           "l2": "inputs larger than L2 (batch is 64 MiB uint8 + 100 MiB of maps per chunk sweep)"}
+           "l2": f"inputs larger than L2 ({B * H * W / 2**20:.0f} MiB uint8 per batch, two batches alternate; "
+                 f"{B * (H // 4) * (W // 4) * 96 * 2 / 2**20:.0f} MiB of maps per sweep)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from oracle import net as onet                       # the reference arm IS the oracle port (TF/Keras absent)
-        imgs = make_images(args.cpu_sample, args.size)
-        xs = onet.preprocess(imgs[:1].astype(np.float64), "mobilenet_like").astype(np.float32)
-        thr = float(np.quantile(onet.forward_torch(weights, xs)[..., 0], 0.9))
-        v, step_s, cores = time_cpu(weights, imgs, thr, max(1, args.steps), max(1, min(args.warmup, 1)))
+        imgs = make_images(args.cpu_sample, H, W)
+        v, step_s, cores = time_cpu(weights, imgs, thr, n_classes, max(1, args.steps), max(1, min(args.warmup, 1)))
+        cfg["reference_arm_batch"] = (f"{args.cpu_sample} images per step (bounded sample of the {B}-image workload; the per-image "
+                                      "rate is what is compared)")
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
-                                 "sample": f"{args.cpu_sample} images of {args.size}x{args.size} per step (torch-CPU "
+                                 "sample": f"{args.cpu_sample} images of {H}x{W} per step (torch-CPU "
                                            "restatement of net.py + the reference's cv2 post-processing; TF/Keras absent)"},
                 "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -259,29 +283,38 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    eng = Engine(device=local_rank, precision=args.precision)
+    eng = Engine(device=local_rank, precision=precision, n_classes=n_classes)
     eng.set_weights(weights)
-    for opt in ("tc_variant", "dense_l2", "stem_chunk"):
+    for opt in ("tc_variant", "dense_l2", "stem_chunk", "stem_variant", "chunk"):
         if os.environ.get("UBD_" + opt.upper()):
             eng.set_option(opt, int(os.environ["UBD_" + opt.upper()]))
-    if os.environ.get("UBD_CHUNK"):
-        eng.set_option("chunk", int(os.environ["UBD_CHUNK"]))
-    B, S = args.batch, args.size
-    imgs = make_images(B, S, seed=1 + rank)
-    pinned = torch.from_numpy(imgs).pin_memory()
-    h_imgs = pinned.numpy()
-    d_imgs = pinned.cuda(non_blocking=False)
-    d_mask = torch.empty((B, S // 4, S // 4), dtype=torch.uint8, device="cuda")
-    d_logits = torch.empty((B, S // 4, S // 4, 1), dtype=torch.float32, device="cuda")
-    # threshold at the 0.9 quantile of this model's logits so ~10 % of the map is positive
-    thr = float(np.quantile(eng.forward(imgs[:2], _lib.PREPROC_MOBILENET)[..., 0], 0.9))
+    # two different batches alternate, so that nothing of step k is still in L2 for step k+1
+    imgs = [make_images(B, H, W, seed=1 + 2 * rank + j) for j in range(2)]
+    pinned = [torch.from_numpy(a).pin_memory() for a in imgs]
+    h_imgs = [p.numpy() for p in pinned]
+    d_imgs = [p.cuda(non_blocking=False) for p in pinned]
     min_area_x2 = 10
+    cap = 256 * B
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
-    def step_dev():
-        return eng.segment_dev(d_imgs.data_ptr(), _lib.UBD_U8, B, S, S, thr, min_area_x2, _lib.PREPROC_MOBILENET,
-                               d_mask.data_ptr(), d_logits.data_ptr())
+    def run_dev(steps):
+        """`steps` batches through the device-resident entry points; returns the last batch's component counts."""
+        counts = None
+        if args.sync_api:
+            for k in range(steps):
+                _, counts = eng.segment_dev(d_imgs[k & 1].data_ptr(), _lib.UBD_U8, B, H, W, thr, min_area_x2, _lib.PREPROC_MOBILENET,
+                                            max_comps=cap)
+            return counts
+        pend = None
+        for k in range(steps):
+            t = eng.segment_submit(None, thr, min_area_x2, _lib.PREPROC_MOBILENET, max_comps=cap,
+                                   device_ptr=d_imgs[k & 1].data_ptr(), shape=(B, H, W), dtype=_lib.UBD_U8)
+            if pend is not None:
+                _, counts = eng.segment_wait(pend)
+            pend = t
+        _, counts = eng.segment_wait(pend)
+        return counts
 
     def barrier():
         if dist is not None:
@@ -290,45 +323,53 @@ def main():
 
     clk = ClockSampler(local_rank)
     clk.__enter__()
-    for _ in range(args.warmup):
-        comps, counts = step_dev()
+    run_dev(args.warmup)
     eng.set_option("profile", 1)
     barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk.mark(True)
     e0.record(stream)
-    for _ in range(args.steps):
-        comps, counts = step_dev()
+    counts = run_dev(args.steps)
     e1.record(stream)
     barrier()
     clk.mark(False)
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
     dil_ms, dil_n = eng.stat("dilconv_ms"), eng.stat("dilconv_launches")
-    stem_ms, ccl_ms, head_ms = eng.stat("stem_ms"), eng.stat("ccl_ms"), eng.stat("head_ms")
+    stem_ms, stem_n = eng.stat("stem_ms"), eng.stat("stem_launches")
+    ccl_ms, head_ms = eng.stat("ccl_ms"), eng.stat("head_ms")
     host_ms = [eng.stat(f"host_ms{i}") / args.steps for i in range(5)]
     eng.set_option("profile", 0)
 
-    # end to end through the host-buffer ABI call (what ModelRunner.predict does)
-    mask_h = torch.empty((B, S // 4, S // 4), dtype=torch.uint8).pin_memory().numpy()
-    def step_e2e():
-        x = h_imgs
-        n = x.shape[0]
-        cap = 64 * n
-        comps_h = np.zeros(cap, _lib.COMPONENT_DTYPE)
-        counts_h = np.zeros(n, np.int32)
-        _lib.check(eng.handle, eng._lib.ubd_segment(eng.handle, _lib.ptr(x), _lib.UBD_U8, n, S, S, _lib.PREPROC_MOBILENET,
-                                                     np.float32(thr), min_area_x2, _lib.ptr(mask_h), None, None,
-                                                     _lib.ptr(comps_h), cap, _lib.ptr(counts_h)))
+    # end to end through the host-buffer C-ABI calls (what ModelRunner.predict / predict_stream do): pinned host
+    # images in, mask + components out, every copy inside the timed region
+    mask_h = [torch.empty((B, H // 4, W // 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+
+    def run_e2e(steps):
+        counts_h = None
+        if args.sync_api:
+            for k in range(steps):
+                comps_h = np.zeros(cap, _lib.COMPONENT_DTYPE)
+                counts_h = np.zeros(B, np.int32)
+                _lib.check(eng.handle, eng._lib.ubd_segment(eng.handle, _lib.ptr(h_imgs[k & 1]), _lib.UBD_U8, B, H, W, _lib.PREPROC_MOBILENET,
+                                                             np.float32(thr), min_area_x2, _lib.ptr(mask_h[k & 1]), None, None,
+                                                             _lib.ptr(comps_h), cap, _lib.ptr(counts_h)))
+            return counts_h
+        pend = None
+        for k in range(steps):
+            t = eng.segment_submit(h_imgs[k & 1], thr, min_area_x2, _lib.PREPROC_MOBILENET, mask_out=mask_h[k & 1], max_comps=cap)
+            if pend is not None:
+                _, counts_h = eng.segment_wait(pend)
+            pend = t
+        _, counts_h = eng.segment_wait(pend)
         return counts_h
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+
+    run_e2e(max(2, args.warmup // 2))
     barrier()
     clk.mark(True)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        counts_h = step_e2e()
+    counts_h = run_e2e(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk.mark(False)
@@ -347,7 +388,7 @@ def main():
         tb = 32
         tx = np.concatenate([synth.synth_images(8, 512, 512, seed=40 + rank)] * (tb // 8))
         ty = np.concatenate([synth.synth_targets(8, 128, 128, 0, seed=40 + rank)] * (tb // 8))
-        model = B200Model(NetConfig(), device=local_rank, weights=weights)
+        model = B200Model(NetConfig(), device=local_rank, weights=usynth.synth_weights(0, seed=1234, calibrated=True))
         model.compile(Adam(1e-3), loss=ulosses.get_loss(False))
         if dist is not None:
             model.set_distributed(True)
@@ -372,59 +413,68 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        q_px = (S // 4) * (S // 4)
-        # dominant kernel = the dilated conv; one launch processes one chunk of images through one layer
-        n_layers = 6
-        imgs_per_launch = B * n_layers * args.steps / max(dil_n, 1)
+        q_px = (H // 4) * (W // 4)
+        tensor_rate = 0.5 if precision in ("fp32", "tf32") else 1.0       # tf32 MMAs run at half the bf16 rate
+        peak_burst, peak_sust = pk["bf16_tflops"] * tensor_rate, pk["bf16_tflops_sustained"] * tensor_rate
+        # the net is compute-bound (AI ~ 965 FLOP/B), so the roofline of the dominant kernel is the tensor pipe.
+        # Dominant kernel = the dilated 3x3 24->24 layer: ALGORITHMIC 2 x 5,184 FLOP per map pixel per layer x the map
+        # pixels one launch processes / its average duration (CUDA events on the launching stream inside the library).
+        imgs_per_launch = B * 6 * args.steps / max(dil_n, 1)
         avg_launch_s = dil_ms / 1e3 / max(dil_n, 1)
-        # tensor view: 10,368 FLOP per map pixel per layer
         flops_per_launch = 2.0 * DIL_MAC_PER_MAP_PX * q_px * imgs_per_launch
         achieved_tf = flops_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
-        peak_tf = pk["bf16_tflops_sustained"] * (0.5 if args.precision in ("fp32", "tf32") else 1.0)
-        # HBM view: a layer launch reads one 24-channel map and writes one (the last one writes logits + mask instead)
-        map_bytes = q_px * 24 * (2 if args.precision == "bf16" else 4)
-        n_out = 1
-        bytes_per_launch = imgs_per_launch * ((n_layers - 1) * 2 * map_bytes + map_bytes + q_px * (4 * n_out + 1)) / n_layers
-        achieved_gbs = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
-        traffic = None
-        try:    # dram bytes of one dilated-layer launch from the committed ncu capture
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))[args.precision]
-            traffic = tj["dram_bytes_per_launch"] * imgs_per_launch * (S * S / 1048576.0) / tj["images_per_launch"]
+        stem_flops_per_step = 2.0 * (33 + 792 + 792 / 4.0) * (H // 2) * (W // 2) * B      # L1 + L2 at half, L3 at quarter resolution
+        traffic, traffic_src, wasted = None, None, None
+        try:    # DRAM bytes from the committed ncu captures of this round (profiles/traffic.json says which)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[precision]
+            scale = imgs_per_launch * (H * W / 1048576.0) / tj["images_per_launch"]
+            traffic = tj["dram_bytes_per_launch"] * scale
+            traffic_src = tj["source"]
+            if "dram_bytes_per_step" in tj:
+                wasted = tj["dram_bytes_per_step"] * (B * H * W / 1048576.0 / tj["images_per_step"]) / (ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0) * B)
         except Exception:
             pass
-        tensor_view = {"achieved_tflops": achieved_tf, "peak_tflops": peak_tf, "frac": achieved_tf / peak_tf if peak_tf else None,
-                       "peak_source": f"{pk['source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s"
-                                      + (" x 0.5 (tf32 rate)" if args.precision in ("fp32", "tf32") else "")}
-        hbm_bound = args.precision != "fp32"       # the tcgen05 kernels stream maps at the HBM rate; the FP32-pipe path is FMA-bound
-        roof = {"bound": "hbm" if hbm_bound else "tensor", "kernel": "dilated 3x3 conv 24->24 (L4-L9), one layer per launch",
-                "achieved": achieved_gbs if hbm_bound else achieved_tf, "peak": pk["hbm_gbs"] if hbm_bound else peak_tf,
-                "unit": "GB/s" if hbm_bound else "TFLOP/s",
-                "frac": (achieved_gbs / pk["hbm_gbs"]) if hbm_bound else (achieved_tf / peak_tf if peak_tf else None),
-                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "peak_source": f"{pk['source']} HBM copy {pk['hbm_gbs']} GB/s" if hbm_bound else tensor_view["peak_source"],
-                "tensor": tensor_view,
-                "avg_launch_us": avg_launch_s * 1e6, "launches": int(dil_n),
+        step_flops = 2.0 * ALGO_MAC_PER_INPUT_PX * H * W * B
+        roof = {"bound": "tensor", "kernel": "tc4::dilconv_col_kernel: dilated 3x3 conv 24->24 (L4-L9), one layer of one chunk per launch",
+                "achieved": achieved_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved_tf / peak_burst if peak_burst else None,
+                "frac_of_sustained_peak": achieved_tf / peak_sust if peak_sust else None,
+                "peak_source": f"{pk['source']} bf16 burst {pk['bf16_tflops']} TF/s (sustained {pk['bf16_tflops_sustained']})"
+                               + (" x 0.5 (tf32 rate)" if tensor_rate == 0.5 else ""),
+                "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6, "launches": int(dil_n),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "share_of_step": dil_ms / ms if ms else None,
-                "hbm_frac_whole_step": ALGO_BYTES_PER_IMAGE_1024 * (S * S / 1048576.0) * (value / world) / (pk["hbm_gbs"] * 1e9),
+                "stem": {"kernels": "tc4::dilconv_col_kernel<L1SRC> (L1+L2) + tc::dilconv_tc_kernel (L3)" if stem_n >= 2 * max(dil_n, 1) / 6 - 0.5
+                                    else "stemf::stem_fused_kernel (L1+L2+L3)",
+                         "ms_per_step": stem_ms / args.steps, "share_of_step": stem_ms / ms if ms else None,
+                         "algorithmic_tflops": stem_flops_per_step / (stem_ms / args.steps / 1e3) / 1e12 if stem_ms else None},
+                "whole_step": {"algorithmic_tflops": step_flops * value / (B * world) / 1e12,
+                               "tensor_frac": step_flops * value / (B * world) / 1e12 / peak_burst if peak_burst else None,
+                               "hbm_frac": ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0) * (value / world) / (pk["hbm_gbs"] * 1e9),
+                               "algorithmic_bytes_per_image": ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0),
+                               "wasted_traffic_ratio": wasted},
+                "cc": {"ms_per_step": ccl_ms / args.steps, "algorithmic_bytes_per_step": 5 * q_px * B,
+                       "hbm_frac": 5 * q_px * B / (ccl_ms / args.steps / 1e3) / (pk["hbm_gbs"] * 1e9) if ccl_ms else None},
                 "stage_ms_per_step": {"stem": stem_ms / args.steps, "dilated": dil_ms / args.steps,
                                       "head": head_ms / args.steps, "ccl": ccl_ms / args.steps},
-                "host_ms_per_step": dict(zip(["enqueue_forward", "enqueue_cc", "sync_counts", "sync_records", "boxes"], host_ms))}
+                "host_ms_per_step": dict(zip(["enqueue_forward", "enqueue_cc", "wait_counts", "read_records", "boxes"], host_ms))}
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[precision],
                 "data": "synthetic", "config": cfg, "clocks": clk.summary(),
-                "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(imgs.nbytes),
-                        "d2h_bytes_per_step": int(mask_h.nbytes + 4 * B + 72 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
-                "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum())}
+                "api": "ubd_segment_dev / ubd_segment" if args.sync_api else "ubd_segment_submit[_dev] + ubd_segment_wait (two batches in flight)",
+                "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(imgs[0].nbytes),
+                        "d2h_bytes_per_step": int(mask_h[0].nbytes + 4 * B + 44 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum()),
+                "components_per_image": float(counts.sum()) / B}
         if not args.no_train:
             line["train_step"] = {"config": "configs[4]: forward + losses.py loss + backward + Adam, batch 32 of 512x512 per GPU, fp32"
                                             + (", gradient all-reduce over NCCL inside libubd (ubd_allreduce_grads)" if world > 1 else ""),
                                   "ms_per_step": train_ms_max, "images_per_sec": 32 * world / (train_ms_max / 1e3),
                                   "loss": train_loss}
         if world == 1 and not args.no_cpu_baseline:
-            v, step_s, cores = time_cpu(weights, imgs[:args.cpu_sample], thr, 3, 1)
+            v, step_s, cores = time_cpu(weights, imgs[0][:args.cpu_sample], thr, n_classes, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
-                                    "sample": f"3 steps x {args.cpu_sample} images of {S}x{S} (torch-CPU restatement + cv2)"}
+                                    "sample": f"3 steps x {args.cpu_sample} images of {H}x{W} (torch-CPU restatement + cv2)"}
         emit(line)
     if dist is not None:
         dist.barrier()

@@ -67,6 +67,22 @@ def test_stress_masks_bit_exact(eng, shape):
     _check_against_spec(eng, masks)
 
 
+@pytest.mark.parametrize("shape", [(12, 40, 56), (6, 256, 256), (2, 544, 960), (3, 17, 33), (2, 1, 70), (2, 50, 1)])
+def test_gpu_rectangles_equal_host_rectangles(shape):
+    """ccl_boxes_kernel (hull + float32 rotating calipers, one warp per component) against the host path
+    (hull candidates -> ubd_min_area_box): every box bit-identical, degenerate components (1 and 2 hull points,
+    collinear pixels) included (min_area -1 keeps everything)."""
+    from ubdvss_b200.engine import Engine
+    e = Engine()
+    masks = synth.stress_masks(*shape, seed=5 + sum(shape))
+    _, a, ca = e.postprocess(masks, None, -1)
+    e.set_option("gpu_boxes", 0)
+    _, b, cb = e.postprocess(masks, None, -1)
+    assert np.array_equal(ca, cb) and len(a) == len(b) > 0
+    assert np.array_equal(a["label"], b["label"])
+    assert np.array_equal(a["box"].view(np.uint32), b["box"].view(np.uint32))
+
+
 def test_degenerate_masks(eng):
     z = np.zeros((2, 32, 32), np.uint8)
     _, comps, counts = eng.postprocess(z, None, 10)

@@ -23,6 +23,9 @@
 
 static std::string g_create_error;
 
+void ubd_box_from_device(float cx, float cy, float w, float hgt, float ax, float ay, int n_hull,
+                         int x0, int y0, int x1, int y1, float* box);      // ubd_rect.cpp
+
 #define LAUNCH_CHECK()                                                     \
   do {                                                                     \
     ++h->launches;                                                         \
@@ -209,6 +212,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   }
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
   else if (!strcmp(name, "stem_variant")) h->opt_stem_variant = (int)value;
+  else if (!strcmp(name, "gpu_boxes")) h->opt_gpu_boxes = value != 0;
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
   else if (!strcmp(name, "stem_chunk")) h->opt_stem_chunk = (int)value;
   else if (!strcmp(name, "tc_trace")) {
@@ -494,7 +498,11 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
   ENSURE(h->out_index, (size_t)n * max_comps * sizeof(int));
   ENSURE(R.hdr, (size_t)(2 * n) * sizeof(int) + sizeof(CclTotals));
   ENSURE(R.out_recs, (size_t)std::max(max_out, 1) * sizeof(OutRec));
-  ENSURE(R.hull_pts, (size_t)max_pts * sizeof(HullPt));
+  // boxes on the GPU unless the map is too tall for the per-warp shared-memory arrays (then: hull candidates + host)
+  const size_t box_smem = ((size_t)12 * mh + 10) * sizeof(int);
+  R.gpu_boxes = h->opt_gpu_boxes && box_smem <= 48 * 1024;
+  if (R.gpu_boxes) ENSURE(R.box_recs, (size_t)std::max(max_out, 1) * sizeof(BoxRec));
+  else ENSURE(R.hull_pts, (size_t)max_pts * sizeof(HullPt));
   const size_t hdr_ints = n + sizeof(CclTotals) / sizeof(int);
   if (R.h_hdr_cap < hdr_ints) {
     if (R.h_hdr) cudaFreeHost(R.h_hdr);
@@ -539,8 +547,14 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
     ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
     ccl_compact_kernel<<<n, 256, 0, h->stream>>>(comps, cls_sums, n_cls, d_ncomps, d_kept, (OutRec*)R.out_recs.p,
                                                  (int*)h->out_index.p, max_comps, max_out, min_area_x2); LAUNCH_CHECK();
-    ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)R.hull_pts.p,
-                                                       d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();
+    if (R.gpu_boxes) {
+      // hull + rotating calipers of every kept component on the GPU, one warp each
+      ccl_boxes_kernel<<<std::max(max_out, 1), 32, box_smem, h->stream>>>(labels, (const OutRec*)R.out_recs.p, d_tot, (BoxRec*)R.box_recs.p,
+                                                                          mh, mw, max_out); LAUNCH_CHECK();
+    } else {
+      ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)R.hull_pts.p,
+                                                         d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();
+    }
   }
   // header: kept counts per image + totals (one small D2H into pinned memory); the records and hull points follow
   // in ccl_finish once their sizes are known
@@ -571,23 +585,42 @@ static int ccl_finish(ubd_handle h, int s, ubd_component* comps_out, int max_out
   }
   if (tot.total_kept > max_out)
     UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_kept) + " kept components exceed the caller's capacity " + std::to_string(max_out));
-  if (tot.total_pts > R.max_pts)
+  if (!R.gpu_boxes && tot.total_pts > R.max_pts)
     UBD_FAIL(UBD_ERR_OVERFLOW, std::to_string(tot.total_pts) + " hull candidate points exceed max_points " + std::to_string(R.max_pts));
   for (int i = 0; i < n; ++i) n_comps_per_image[i] = R.h_hdr[i];
   if (tot.total_kept == 0) return UBD_OK;
   std::vector<OutRec>& recs = R.recs;
   std::vector<HullPt>& pts = R.pts;
+  std::vector<BoxRec>& boxes = R.boxes;
   {
     HostTimer ht_s2(h, 3);
     recs.resize(tot.total_kept);
-    pts.resize(tot.total_pts);
+    pts.resize(R.gpu_boxes ? 0 : tot.total_pts);
+    boxes.resize(R.gpu_boxes ? tot.total_kept : 0);
     // on the read-back stream: the handle's own stream may already hold the next batch's kernels
     UBD_CUDA(cudaMemcpyAsync(recs.data(), R.out_recs.p, recs.size() * sizeof(OutRec), cudaMemcpyDeviceToHost, h->d2h_stream));
     if (!pts.empty())
       UBD_CUDA(cudaMemcpyAsync(pts.data(), R.hull_pts.p, pts.size() * sizeof(HullPt), cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (!boxes.empty())
+      UBD_CUDA(cudaMemcpyAsync(boxes.data(), R.box_recs.p, boxes.size() * sizeof(BoxRec), cudaMemcpyDeviceToHost, h->d2h_stream));
     UBD_CUDA(cudaStreamSynchronize(h->d2h_stream));
   }
   HostTimer ht_host(h, 4);
+  auto fill = [&](int i) -> ubd_component& {
+    const OutRec& r = recs[i];
+    ubd_component& c = comps_out[i];
+    c.image = r.image; c.label = r.label; c.xmin = r.xmin; c.ymin = r.ymin; c.xmax = r.xmax; c.ymax = r.ymax;
+    c.n_pixels = r.n_pixels; c.n_filled = r.n_filled; c.area_x2 = r.area_x2; c.class_id = r.class_id;
+    return c;
+  };
+  if (R.gpu_boxes) {
+    // the GPU left centre, size and first edge vector of every rectangle: only cv2.boxPoints' trigonometry remains
+    for (int i = 0; i < tot.total_kept; ++i) {
+      const BoxRec& b = boxes[i];
+      ubd_box_from_device(b.cx, b.cy, b.w, b.h, b.ax, b.ay, b.n_hull, b.x0, b.y0, b.x1, b.y1, fill(i).box);
+    }
+    return UBD_OK;
+  }
   // Reduce the hull candidates to the leftmost / rightmost one per (component, row) -- only those can
   // be hull vertices -- then the min-area box of each component on the host.
   std::vector<int>& row0 = R.row0;
@@ -605,9 +638,7 @@ static int ccl_finish(ubd_handle h, int s, ubd_component* comps_out, int max_out
   std::vector<int32_t>& xy = R.xy;
   for (int i = 0; i < tot.total_kept; ++i) {
     const OutRec& r = recs[i];
-    ubd_component& c = comps_out[i];
-    c.image = r.image; c.label = r.label; c.xmin = r.xmin; c.ymin = r.ymin; c.xmax = r.xmax; c.ymax = r.ymax;
-    c.n_pixels = r.n_pixels; c.n_filled = r.n_filled; c.area_x2 = r.area_x2; c.class_id = r.class_id;
+    ubd_component& c = fill(i);
     xy.clear();
     for (int y = r.ymin; y <= r.ymax; ++y) {
       const int* e = &ext[2 * (size_t)(row0[i] + y - r.ymin)];

@@ -516,3 +516,164 @@ ccl_points_kernel(const int* __restrict__ labels, const int* __restrict__ slot_o
     if (idx < max_pts) { HullPt p; p.comp = comp; p.xy = (y << 16) | x; pts[idx] = p; }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Min-area rectangle of every kept component on the GPU (utils.py:56-57, cv2.minAreaRect): one warp per
+// component.  (1) the warp scans the component's bounding box in the filled label image for the left- and
+// right-most pixel of every row - only those can be hull vertices; (2) lane 0 builds the strict convex hull
+// from the two y-monotone chains (integer cross products) in the order ubd_rect.cpp feeds the calipers:
+// top edge left to right, right side down, bottom edge right to left, left side up, ENDING at the top-most,
+// then left-most pixel (the contour's first point); (3) lane 0 runs the float32 rotating calipers with exactly
+// the host's operation order (explicit round-to-nearest intrinsics: no FMA contraction, double sqrt / divide
+// are IEEE on both sides), so the six numbers it leaves are bit-identical to ubd_min_area_box's.  The host only
+// adds the angle / corner trigonometry of cv2.boxPoints (libm), a few hundred nanoseconds per component.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ long long ccl_cross(int ox, int oy, int ax, int ay, int bx, int by) {
+  return (long long)(ax - ox) * (by - oy) - (long long)(ay - oy) * (bx - ox);
+}
+
+__global__ void __launch_bounds__(32)
+ccl_boxes_kernel(const int* __restrict__ labels, const OutRec* __restrict__ recs, const CclTotals* __restrict__ totals,
+                 BoxRec* __restrict__ boxes, int h, int w, int max_out) {
+  extern __shared__ int box_smem[];
+  const int comp = blockIdx.x, lane = threadIdx.x;
+  if (comp >= min(totals->total_kept, max_out)) return;
+  const OutRec r = recs[comp];
+  const int rows = r.ymax - r.ymin + 1;
+  int* L = box_smem;                       // [rows]
+  int* R = L + h;                          // [rows]
+  int* hx = R + h;                         // [2 * rows + 2]
+  int* hy = hx + 2 * h + 2;
+  float* vx = reinterpret_cast<float*>(hy + 2 * h + 2);
+  float* vy = vx + 2 * h + 2;
+  float* inv = vy + 2 * h + 2;
+  const int* lab = labels + (size_t)r.image * h * w;
+  // (1) row extents
+  for (int y = r.ymin; y <= r.ymax; ++y) {
+    int lo = 0x7fffffff, hi = -1;
+    for (int x0 = r.xmin; x0 <= r.xmax; x0 += 32) {
+      const int x = x0 + lane;
+      const bool in = x <= r.xmax && lab[(size_t)y * w + x] == r.label;
+      const unsigned b = __ballot_sync(0xffffffffu, in);
+      if (b) {
+        if (lo == 0x7fffffff) lo = x0 + __ffs(b) - 1;
+        hi = x0 + 31 - __clz(b);
+      }
+    }
+    if (lane == 0) { L[y - r.ymin] = lo; R[y - r.ymin] = hi; }
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  // (2) hull.  Every row of an 8-connected filled component between ymin and ymax holds at least one pixel.
+  int k = 0;
+  for (int i = 0; i < rows; ++i) {                       // right side, top to bottom
+    const int px = R[i], py = r.ymin + i;
+    while (k >= 2 && ccl_cross(hx[k - 2], hy[k - 2], hx[k - 1], hy[k - 1], px, py) <= 0) --k;
+    hx[k] = px; hy[k] = py; ++k;
+  }
+  const int t = k + 1;
+  for (int i = rows - 1; i >= 0; --i) {                  // left side, bottom to top
+    const int px = L[i], py = r.ymin + i;
+    if (hx[k - 1] == px && hy[k - 1] == py) continue;
+    while (k >= t && ccl_cross(hx[k - 2], hy[k - 2], hx[k - 1], hy[k - 1], px, py) <= 0) --k;
+    hx[k] = px; hy[k] = py; ++k;
+  }
+  if (k > 1 && hx[k - 1] == hx[0] && hy[k - 1] == hy[0]) {
+    // single-pixel top row: the walk started at the contour's first point; it has to come last
+    --k;
+    const int fx = hx[0], fy = hy[0];
+    for (int i = 0; i + 1 < k; ++i) { hx[i] = hx[i + 1]; hy[i] = hy[i + 1]; }
+    hx[k - 1] = fx; hy[k - 1] = fy;
+  }
+  const int n = k;
+  BoxRec o;
+  o.n_hull = n; o.x0 = hx[0]; o.y0 = hy[0]; o.x1 = n > 1 ? hx[1] : hx[0]; o.y1 = n > 1 ? hy[1] : hy[0];
+  o.cx = o.cy = o.w = o.h = o.ax = o.ay = 0.f;
+  if (n > 2) {
+    // (3) rotating calipers (cv2 rotatingCalipers, CALIPERS_MINAREARECT), float32, host operation order
+    float minarea = 3.402823466e+38f;
+    int left = 0, bottom = 0, right = 0, top = 0;
+    float orientation = 0.f, base_a, base_b = 0.f;
+    float p0x = (float)hx[0], p0y = (float)hy[0];
+    float left_x = p0x, right_x = p0x, top_y = p0y, bottom_y = p0y;
+    for (int i = 0; i < n; ++i) {
+      if (p0x < left_x) { left_x = p0x; left = i; }
+      if (p0x > right_x) { right_x = p0x; right = i; }
+      if (p0y > top_y) { top_y = p0y; top = i; }
+      if (p0y < bottom_y) { bottom_y = p0y; bottom = i; }
+      const int j = (i + 1 < n) ? i + 1 : 0;
+      const float qx = (float)hx[j], qy = (float)hy[j];
+      const double dx = (double)qx - (double)p0x, dy = (double)qy - (double)p0y;
+      vx[i] = (float)dx; vy[i] = (float)dy;
+      inv[i] = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)))));
+      p0x = qx; p0y = qy;
+    }
+    {
+      double ax = vx[n - 1], ay = vy[n - 1];
+      for (int i = 0; i < n; ++i) {
+        const double bx = vx[i], by = vy[i];
+        const double convexity = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+        if (convexity != 0) { orientation = convexity > 0 ? 1.f : -1.f; break; }
+        ax = bx; ay = by;
+      }
+    }
+    base_a = orientation;
+    int seq[4] = {bottom, right, top, left};
+    int best_left = 0, best_bottom = 0;
+    float best_a = 1.f, best_b = 0.f, best_w = 0.f, best_h = 0.f;
+    for (int it = 0; it < n; ++it) {
+      float dp[4];
+      dp[0] = __fadd_rn(__fmul_rn(base_a, vx[seq[0]]), __fmul_rn(base_b, vy[seq[0]]));
+      dp[1] = __fadd_rn(__fmul_rn(-base_b, vx[seq[1]]), __fmul_rn(base_a, vy[seq[1]]));
+      dp[2] = __fsub_rn(__fmul_rn(-base_a, vx[seq[2]]), __fmul_rn(base_b, vy[seq[2]]));
+      dp[3] = __fsub_rn(__fmul_rn(base_b, vx[seq[3]]), __fmul_rn(base_a, vy[seq[3]]));
+      float maxcos = __fmul_rn(dp[0], inv[seq[0]]);
+      int main_element = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        const float cosalpha = __fmul_rn(dp[i], inv[seq[i]]);
+        if (cosalpha > maxcos) { main_element = i; maxcos = cosalpha; }
+      }
+      {
+        const int pindex = seq[main_element];
+        const float lead_x = __fmul_rn(vx[pindex], inv[pindex]);
+        const float lead_y = __fmul_rn(vy[pindex], inv[pindex]);
+        switch (main_element) {
+          case 0: base_a = lead_x; base_b = lead_y; break;
+          case 1: base_a = lead_y; base_b = -lead_x; break;
+          case 2: base_a = -lead_x; base_b = -lead_y; break;
+          default: base_a = -lead_y; base_b = lead_x; break;
+        }
+      }
+      seq[main_element] += 1;
+      if (seq[main_element] == n) seq[main_element] = 0;
+      float dx = __fsub_rn((float)hx[seq[1]], (float)hx[seq[3]]);
+      float dy = __fsub_rn((float)hy[seq[1]], (float)hy[seq[3]]);
+      const float width = __fadd_rn(__fmul_rn(dx, base_a), __fmul_rn(dy, base_b));
+      dx = __fsub_rn((float)hx[seq[2]], (float)hx[seq[0]]);
+      dy = __fsub_rn((float)hy[seq[2]], (float)hy[seq[0]]);
+      const float height = __fadd_rn(__fmul_rn(-dx, base_b), __fmul_rn(dy, base_a));
+      const float area = __fmul_rn(width, height);
+      if (area <= minarea) {
+        minarea = area;
+        best_left = seq[3]; best_a = base_a; best_w = width; best_b = base_b; best_h = height;
+        best_bottom = seq[0];
+      }
+    }
+    const float A1 = best_a, B1 = best_b, A2 = -best_b, B2 = best_a;
+    const float C1 = __fadd_rn(__fmul_rn(A1, (float)hx[best_left]), __fmul_rn((float)hy[best_left], B1));
+    const float C2 = __fadd_rn(__fmul_rn(A2, (float)hx[best_bottom]), __fmul_rn((float)hy[best_bottom], B2));
+    const float idet = __fdiv_rn(1.f, __fsub_rn(__fmul_rn(A1, B2), __fmul_rn(A2, B1)));
+    const float o0x = __fmul_rn(__fsub_rn(__fmul_rn(C1, B2), __fmul_rn(C2, B1)), idet);
+    const float o0y = __fmul_rn(__fsub_rn(__fmul_rn(A1, C2), __fmul_rn(A2, C1)), idet);
+    const float o1x = __fmul_rn(A1, best_w), o1y = __fmul_rn(B1, best_w);
+    const float o2x = __fmul_rn(A2, best_h), o2y = __fmul_rn(B2, best_h);
+    o.cx = __fadd_rn(o0x, __fmul_rn(__fadd_rn(o1x, o2x), 0.5f));
+    o.cy = __fadd_rn(o0y, __fmul_rn(__fadd_rn(o1y, o2y), 0.5f));
+    o.w = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn((double)o1x, (double)o1x), __dmul_rn((double)o1y, (double)o1y))));
+    o.h = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn((double)o2x, (double)o2x), __dmul_rn((double)o2y, (double)o2y))));
+    o.ax = o1x; o.ay = o1y;
+  }
+  boxes[comp] = o;
+}

@@ -56,6 +56,9 @@ struct OutRec {
   int image, label, xmin, ymin, xmax, ymax, n_pixels, n_filled, area_x2, class_id, slot;
 };
 struct CclTotals { int total_kept, total_pts, max_ncomp, pad; };
+// min-area rectangle of a kept component as ccl_boxes_kernel leaves it (centre, size, first edge vector, hull size
+// and its first two points for the degenerate cases)
+struct BoxRec { float cx, cy, w, h, ax, ay; int n_hull, x0, y0, x1, y1; };
 struct HullPt { int comp; int xy; };     // comp = index into the compacted output; xy = (y << 16) | x
 
 #define UBD_CUDA(call)                                                                      \

@@ -8,7 +8,8 @@ struct DevBuf { void* p = nullptr; size_t cap = 0; };
 // Host-visible results of one batch (see ccl_enqueue / ccl_finish in ubd_api.cu): two slots so that a submitted batch
 // can be finished on the host while the next one runs.
 struct ResultSlot {
-  DevBuf hdr, out_recs, hull_pts;          // device: raw / kept counts + totals, kept records, hull candidates
+  DevBuf hdr, out_recs, hull_pts, box_recs;          // device: raw / kept counts + totals, kept records, hull candidates | rectangles
+  bool gpu_boxes = true;
   DevBuf d_images, d_mask, d_logits;       // device: staging of a submitted batch and its outputs
   int* h_hdr = nullptr; size_t h_hdr_cap = 0;     // pinned copy of hdr (kept counts + totals)
   cudaEvent_t ev_cc = nullptr, ev_fwd = nullptr;
@@ -17,7 +18,7 @@ struct ResultSlot {
   int cls_stride = 0, n_cls = 0, min_area_x2 = 0;
   bool busy = false;
   long long ticket = 0;
-  std::vector<OutRec> recs; std::vector<HullPt> pts;      // host scratch, reused
+  std::vector<OutRec> recs; std::vector<HullPt> pts; std::vector<BoxRec> boxes;      // host scratch, reused
   std::vector<int> row0, ext; std::vector<int32_t> xy;
 };
 
@@ -58,6 +59,7 @@ struct ubd_handle_s {
   int opt_chunk = 0;              // images per L2-resident chunk (0 = auto)
   int opt_max_comps = 4096;       // component slots per image
   int opt_max_points = 0;         // hull candidate capacity (0 = auto)
+  int opt_gpu_boxes = 1;          // min-area rectangles on the GPU (0: hull candidates to the host, ubd_min_area_box)
 
   // inference workspaces
   DevBuf d_images, d_logits, d_mask;
@@ -84,7 +86,7 @@ struct ubd_handle_s {
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &out_index, &rs[0].hdr, &rs[0].out_recs, &rs[0].hull_pts, &rs[0].d_images, &rs[0].d_mask, &rs[0].d_logits,
+            &cls_sums, &out_index, &rs[0].hdr, &rs[0].out_recs, &rs[0].hull_pts, &rs[0].box_recs, &rs[1].box_recs, &rs[0].d_images, &rs[0].d_mask, &rs[0].d_logits,
             &rs[1].hdr, &rs[1].out_recs, &rs[1].hull_pts, &rs[1].d_images, &rs[1].d_mask, &rs[1].d_logits, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
   }

@@ -144,6 +144,44 @@ void rotating_calipers(const P2f* points, int n, P2f out[3]) {
 
 }  // namespace
 
+// RotatedRect (angle in radians as minAreaRect leaves it before the degree conversion) -> cv2.boxPoints corners.
+void ubd_rect_to_box(float cx, float cy, float w, float hgt, float angle, float* box) {
+  angle = (float)(angle * 180 / 3.1415926535897932384626433832795);
+  // RotatedRect::points
+  const double a_ = angle * 3.1415926535897932384626433832795 / 180.;
+  const float b = (float)cos(a_) * 0.5f;
+  const float a = (float)sin(a_) * 0.5f;
+  box[0] = cx - a * hgt - b * w;
+  box[1] = cy + b * hgt - a * w;
+  box[2] = cx + a * hgt - b * w;
+  box[3] = cy - b * hgt - a * w;
+  box[4] = 2 * cx - box[0];
+  box[5] = 2 * cy - box[1];
+  box[6] = 2 * cx - box[2];
+  box[7] = 2 * cy - box[3];
+}
+
+// The rectangle of a component whose hull and calipers were computed on the GPU (ccl_boxes_kernel): ax, ay = the
+// first edge vector (out[1] of rotatingCalipers); n_hull <= 2: the degenerate cases from the hull's end points.
+void ubd_box_from_device(float cx, float cy, float w, float hgt, float ax, float ay, int n_hull,
+                         int x0, int y0, int x1, int y1, float* box) {
+  float angle = 0.f;
+  if (n_hull > 2) {
+    angle = (float)atan2((double)ay, (double)ax);
+  } else if (n_hull == 2) {
+    if (x1 < x0 || (x1 == x0 && y1 < y0)) { std::swap(x0, x1); std::swap(y0, y1); }     // the host hull lists them by (x, y)
+    cx = ((float)x0 + (float)x1) * 0.5f;
+    cy = ((float)y0 + (float)y1) * 0.5f;
+    const double dx = (double)x1 - x0, dy = (double)y1 - y0;
+    w = (float)sqrt(dx * dx + dy * dy);
+    hgt = 0.f;
+    angle = (float)atan2(dy, dx);
+  } else {
+    cx = (float)x0; cy = (float)y0; w = hgt = 0.f;
+  }
+  ubd_rect_to_box(cx, cy, w, hgt, angle, box);
+}
+
 // pts: any superset of the component's hull vertices (e.g. its row-run end points).
 extern "C" int ubd_min_area_box(const int32_t* pts_xy, int n_pts, float* box) {
   if (box == nullptr || (n_pts > 0 && pts_xy == nullptr) || n_pts < 0) return UBD_ERR_ARG;
@@ -173,18 +211,6 @@ extern "C" int ubd_min_area_box(const int32_t* pts_xy, int n_pts, float* box) {
   } else if (n == 1) {
     cx = (float)hull[0].x; cy = (float)hull[0].y;
   }
-  angle = (float)(angle * 180 / 3.1415926535897932384626433832795);
-  // RotatedRect::points
-  const double a_ = angle * 3.1415926535897932384626433832795 / 180.;
-  const float b = (float)cos(a_) * 0.5f;
-  const float a = (float)sin(a_) * 0.5f;
-  box[0] = cx - a * hgt - b * w;
-  box[1] = cy + b * hgt - a * w;
-  box[2] = cx + a * hgt - b * w;
-  box[3] = cy - b * hgt - a * w;
-  box[4] = 2 * cx - box[0];
-  box[5] = 2 * cy - box[1];
-  box[6] = 2 * cx - box[2];
-  box[7] = 2 * cy - box[3];
+  ubd_rect_to_box(cx, cy, w, hgt, angle, box);
   return UBD_OK;
 }

@@ -99,10 +99,77 @@ def synth_targets(n, h, w, n_classes=0, seed=0):
     return out
 
 
-def synth_weights(n_classes=0, seed=1234, grey=True, bias_std=0.1):
+def _calibration_forward(ws, x, fml=True):
+    """Pre-activations of every layer of net.py:286-313 for weight calibration (NumPy, small image only)."""
+    def pad(a, t, b, l, r):
+        return np.pad(a, ((t, b), (l, r), (0, 0)))
+
+    def depthwise(a, k, stride, pads):
+        ap = pad(a, *pads)
+        ho, wo = (ap.shape[0] - 3) // stride + 1, (ap.shape[1] - 3) // stride + 1
+        out = np.zeros((ho, wo, a.shape[2]), np.float32)
+        for i in range(3):
+            for j in range(3):
+                out += ap[i:i + stride * (ho - 1) + 1:stride, j:j + stride * (wo - 1) + 1:stride] * k[i, j, :, 0]
+        return out
+
+    def conv(a, k, d):
+        h, w = a.shape[:2]
+        ap = pad(a, d, d, d, d)
+        out = np.zeros((h, w, k.shape[3]), np.float32)
+        for i in range(3):
+            for j in range(3):
+                out += ap[i * d:i * d + h, j * d:j * d + w] @ k[i, j]
+        return out
+
+    s2 = (1, 0, 1, 0) if fml else (0, 1, 0, 1)
+    for li, (stride, pads) in enumerate(((2, s2), (1, (1, 1, 1, 1)), (2, s2))):
+        z = depthwise(x, ws[3 * li], stride, pads) @ ws[3 * li + 1][0, 0] + ws[3 * li + 2]
+        x = yield li, z
+    for li, d in enumerate((1, 2, 4, 8, 16, 1)):
+        z = conv(x, ws[9 + 2 * li], d) + ws[10 + 2 * li]
+        x = yield 3 + li, z
+    yield 9, x @ ws[21][0, 0] + ws[22]
+
+
+def _calibrate(ws, grey, seed):
+    """Layer-sequential unit-variance scaling (LSUV, Mishkin & Matas 2016) on one synthetic image: random Glorot
+    kernels make this net's logit map spatially constant (its random-sign sums average the content away), so every
+    layer's kernel is rescaled per output channel to unit spatial variance of its pre-activation and its bias
+    centres a random quantile (20-80 %) at zero.  The detection logit ends with std 2 and its 0.9 quantile at 0
+    (about 10 % positive pixels at pixel_threshold 0.5), class logits with std 2, mean 0."""
+    rng = np.random.default_rng(seed + 7919)
+    img = synth_images(1, 384, 384, seed=seed + 31, channels=1 if grey else 3)[0].astype(np.float32)
+    x = (img - 127.5) / 127.5
+    gen = _calibration_forward(ws, x)
+    li, z = next(gen)
+    while True:
+        m = z.reshape(-1, z.shape[-1])
+        if li < 9:
+            ki, bi = (3 * li + 1, 3 * li + 2) if li < 3 else (9 + 2 * (li - 3), 10 + 2 * (li - 3))
+            sd = m.std(0) + 1e-6
+            ws[ki] = (ws[ki] / sd).astype(np.float32)
+            zn = (m - ws[bi]) / sd
+            q = np.array([np.quantile(zn[:, c], rng.uniform(0.2, 0.8)) for c in range(zn.shape[1])], np.float32)
+            ws[bi] = (-q).astype(np.float32)
+            li, z = gen.send(np.maximum(zn - q, 0).reshape(z.shape).astype(np.float32))
+        else:
+            sd = m.std(0) + 1e-6
+            ws[21] = (ws[21] * (2.0 / sd)).astype(np.float32)
+            zn = (m - ws[22]) * (2.0 / sd)
+            off = zn.mean(0)
+            off[0] = np.quantile(zn[:, 0], 0.9)
+            ws[22] = (-off).astype(np.float32)
+            break
+    return ws
+
+
+def synth_weights(n_classes=0, seed=1234, grey=True, bias_std=0.1, calibrated=False):
     """Random-init weights of the architecture (no checkpoints ship with the reference): Glorot-uniform
     kernels as Keras initialises them (net.py:226) and N(0, bias_std) biases so that the bias paths are
-    exercised; the 23 arrays in ``get_weights()`` order."""
+    exercised; the 23 arrays in ``get_weights()`` order.  ``calibrated``: rescale them layer by layer
+    (``_calibrate``) so that the logit map responds to the image content - the workload of bench.py and of the
+    full-size parity tests."""
     from .engine import weight_shapes
     rng = np.random.default_rng(seed)
     out = []
@@ -113,4 +180,6 @@ def synth_weights(n_classes=0, seed=1234, grey=True, bias_std=0.1):
             kh, kw, cin, cout = shape
             limit = np.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
             out.append(rng.uniform(-limit, limit, size=shape).astype(np.float32))
+    if calibrated:
+        out = _calibrate(out, grey, seed)
     return out
