@@ -83,6 +83,20 @@ def test_gpu_rectangles_equal_host_rectangles(shape):
     assert np.array_equal(a["box"].view(np.uint32), b["box"].view(np.uint32))
 
 
+@pytest.mark.parametrize("shape", [(12, 40, 56), (6, 256, 256), (3, 17, 33), (2, 1, 70), (2, 50, 1), (1, 128, 512)])
+def test_whole_image_kernel_bit_exact(shape):
+    """Option fused_ccl 1: maps of up to 65,536 px are labelled by one CTA per image in shared memory
+    (ccl_image_kernel); same labels, records and boxes as the default tiled multi-kernel path."""
+    from ubdvss_b200.engine import Engine
+    e = Engine()
+    e.set_option("fused_ccl", 0)
+    masks = synth.stress_masks(*shape, seed=sum(shape))
+    comps_t, counts_t = _check_against_spec(e, masks)
+    e.set_option("fused_ccl", 1)
+    comps_f, counts_f = _check_against_spec(e, masks)
+    assert np.array_equal(counts_t, counts_f) and np.array_equal(comps_t, comps_f)
+
+
 def test_degenerate_masks(eng):
     z = np.zeros((2, 32, 32), np.uint8)
     _, comps, counts = eng.postprocess(z, None, 10)

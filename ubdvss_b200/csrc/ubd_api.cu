@@ -139,6 +139,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   tc4_setup_attributes();
   stem_setup_attributes();
   stemf_setup_attributes();
+  cudaFuncSetAttribute(ccl_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_image_smem(CCL_IMG_MAX_PX));
   *out = h;
   return UBD_OK;
 }
@@ -213,6 +214,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
   else if (!strcmp(name, "stem_variant")) h->opt_stem_variant = (int)value;
   else if (!strcmp(name, "gpu_boxes")) h->opt_gpu_boxes = value != 0;
+  else if (!strcmp(name, "fused_ccl")) h->opt_fused_ccl = value != 0;
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
   else if (!strcmp(name, "stem_chunk")) h->opt_stem_chunk = (int)value;
   else if (!strcmp(name, "tc_trace")) {
@@ -489,8 +491,11 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
   const size_t pstride = (npx + 1 + 31) & ~(size_t)31;
   const int max_comps = h->opt_max_comps;
   const int max_pts = h->opt_max_points > 0 ? h->opt_max_points : (int)std::min<size_t>((size_t)n * npx / 2 + 1024, (size_t)1 << 26);
-  ENSURE(h->parent, (size_t)n * pstride * sizeof(int));
-  ENSURE(h->outer, (size_t)n * pstride);
+  const bool fused = h->opt_fused_ccl && npx <= (size_t)CCL_IMG_MAX_PX;
+  if (!fused) {
+    ENSURE(h->parent, (size_t)n * pstride * sizeof(int));
+    ENSURE(h->outer, (size_t)n * pstride);
+  }
   ENSURE(h->labels, (size_t)n * npx * sizeof(int));
   ENSURE(h->slot_of, (size_t)n * npx * sizeof(int));
   ENSURE(h->comps, (size_t)n * max_comps * sizeof(CompRec));
@@ -528,23 +533,30 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
     HostTimer ht_enq(h, 1);
     ProfScope ps_ccl(h, &h->prof_ccl);
     UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
-    dim3 lgrid32((mw + CCL_T - 1) / CCL_T, (mh + CCL_T - 1) / CCL_T, n);
-    ccl_local_kernel<<<lgrid32, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
-    const int n_border = ((mh - 1) / CCL_T) * mw + ((mw - 1) / CCL_T) * 2 * mh;
-    if (n_border > 0) {
-      dim3 bgrid2((unsigned)((n_border + 255) / 256), n);
-      ccl_border_kernel<<<bgrid2, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+    if (fused) {
+      // one CTA per image, everything in shared memory (ubd_ccl.cuh, "whole-image variant")
+      ccl_image_kernel<<<n, CCL_IMG_THREADS, ccl_image_smem((int)npx), h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls,
+                                                                                   d_ncomps, d_kept, d_tot, mh, mw, max_comps, min_area_x2);
+      LAUNCH_CHECK();
+    } else {
+      dim3 lgrid32((mw + CCL_T - 1) / CCL_T, (mh + CCL_T - 1) / CCL_T, n);
+      ccl_local_kernel<<<lgrid32, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+      const int n_border = ((mh - 1) / CCL_T) * mw + ((mw - 1) / CCL_T) * 2 * mh;
+      if (n_border > 0) {
+        dim3 bgrid2((unsigned)((n_border + 255) / 256), n);
+        ccl_border_kernel<<<bgrid2, 256, 0, h->stream>>>(d_mask, parent, mh, mw, pstride); LAUNCH_CHECK();
+      }
+      uint8_t* outer = (uint8_t*)h->outer.p;
+      ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+      dim3 bgrid((unsigned)((2 * (mh + mw) + 255) / 256), n);
+      ccl_mark_outer_kernel<<<bgrid, 256, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+      ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
+      ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, outer, labels, mh, mw, pstride); LAUNCH_CHECK();
+      ccl_slots_kernel<<<n, 1024, 0, h->stream>>>(labels, slot_of, comps, cls_sums, n_cls, d_ncomps, mh, mw, max_comps); LAUNCH_CHECK();
+      dim3 sgrid((mw + 1 + 31) / 32, (mh + 1 + 7) / 8, n);
+      ccl_stats_kernel<<<sgrid, tblock, 0, h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls, mh, mw, max_comps); LAUNCH_CHECK();
+      ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
     }
-    uint8_t* outer = (uint8_t*)h->outer.p;
-    ccl_flatten_kernel<<<lgrid, 256, 0, h->stream>>>(parent, outer, mh, mw, pstride); LAUNCH_CHECK();
-    dim3 bgrid((unsigned)((2 * (mh + mw) + 255) / 256), n);
-    ccl_mark_outer_kernel<<<bgrid, 256, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
-    ccl_merge2_kernel<<<tgrid, tblock, 0, h->stream>>>(d_mask, parent, outer, mh, mw, pstride); LAUNCH_CHECK();
-    ccl_label_kernel<<<lgrid, 256, 0, h->stream>>>(d_mask, parent, outer, labels, mh, mw, pstride); LAUNCH_CHECK();
-    ccl_slots_kernel<<<n, 1024, 0, h->stream>>>(labels, slot_of, comps, cls_sums, n_cls, d_ncomps, mh, mw, max_comps); LAUNCH_CHECK();
-    dim3 sgrid((mw + 1 + 31) / 32, (mh + 1 + 7) / 8, n);
-    ccl_stats_kernel<<<sgrid, tblock, 0, h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls, mh, mw, max_comps); LAUNCH_CHECK();
-    ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
     ccl_compact_kernel<<<n, 256, 0, h->stream>>>(comps, cls_sums, n_cls, d_ncomps, d_kept, (OutRec*)R.out_recs.p,
                                                  (int*)h->out_index.p, max_comps, max_out, min_area_x2); LAUNCH_CHECK();
     if (R.gpu_boxes) {

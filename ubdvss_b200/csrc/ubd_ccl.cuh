@@ -677,3 +677,301 @@ ccl_boxes_kernel(const int* __restrict__ labels, const OutRec* __restrict__ recs
   }
   boxes[comp] = o;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Whole-image variant: maps of up to 65,536 pixels (a 1024x1024 input's 256x256 map) are labelled by ONE
+// CTA with everything in shared memory - 16-bit parents (the raster index fits), the mask bytes, one bit per
+// pixel for "outer background root" and "filled" - so the eight passes of the algorithm above are separated
+// by __syncthreads instead of kernel launches and no tile-border merge exists.  The kernel also ranks the
+// roots, accumulates the component records and counts the kept ones; compaction and the rectangles follow
+// (3 launches per batch instead of 12).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf16_find(const uint16_t* par, int i) {
+  int p;
+  while ((p = *((volatile const uint16_t*)(par + i))) != i) i = p;
+  return i;
+}
+// find with path halving: a non-root is re-pointed at its grandparent with a plain store.  Only non-roots are written
+// and only with one of their ancestors, so the race with the 32-bit CAS of atomic_min16 on the neighbouring half-word
+// is benign (a lost or repeated store leaves a valid, possibly longer, chain).
+__device__ __forceinline__ int uf16_find_halve(uint16_t* par, int i) {
+  while (true) {
+    const int p = *((volatile uint16_t*)(par + i));
+    if (p == i) return i;
+    const int g = *((volatile uint16_t*)(par + p));
+    if (g == p) return p;
+    *((volatile uint16_t*)(par + i)) = (uint16_t)g;
+    i = g;
+  }
+}
+__device__ __forceinline__ int atomic_min16(uint16_t* addr, int val) {
+  unsigned* wp = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
+  const unsigned shift = (reinterpret_cast<uintptr_t>(addr) & 2) ? 16u : 0u;
+  unsigned cur = *((volatile unsigned*)wp);
+  while (true) {
+    const int old = (int)((cur >> shift) & 0xFFFFu);
+    if (old <= val) return old;
+    const unsigned nw = (cur & ~(0xFFFFu << shift)) | ((unsigned)val << shift);
+    const unsigned prev = atomicCAS(wp, cur, nw);
+    if (prev == cur) return old;
+    cur = prev;
+  }
+}
+__device__ __forceinline__ void uf16_union(uint16_t* par, int a, int b) {
+  while (true) {
+    a = uf16_find_halve(par, a);
+    b = uf16_find_halve(par, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    const int old = atomic_min16(par + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+constexpr int CCL_IMG_THREADS = 1024;
+constexpr int CCL_IMG_MAX_PX = 65536;
+static inline size_t ccl_image_smem(int hw) {
+  const size_t words = ((size_t)hw + 31) / 32;
+  return (((size_t)hw * 2 + 15) & ~(size_t)15) + (((size_t)hw + 15) & ~(size_t)15) + 2 * words * 4 + 512;
+}
+
+__global__ void __launch_bounds__(CCL_IMG_THREADS, 1)
+ccl_image_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels, int* __restrict__ slot_of,
+                 CompRec* __restrict__ comps, const float* __restrict__ cls_logits, int cls_stride,
+                 unsigned long long* __restrict__ cls_sums, int n_cls, int* __restrict__ n_comps,
+                 int* __restrict__ kept_count, CclTotals* __restrict__ totals, int h, int w, int max_comps, int min_area_x2) {
+  extern __shared__ __align__(16) uint8_t ccl_smem[];
+  const int hw = h * w;
+  const int words = (hw + 31) / 32;
+  uint16_t* par = reinterpret_cast<uint16_t*>(ccl_smem);
+  uint8_t* m = ccl_smem + (((size_t)hw * 2 + 15) & ~(size_t)15);
+  unsigned* outer = reinterpret_cast<unsigned*>(m + (((size_t)hw + 15) & ~(size_t)15));
+  unsigned* filled = outer + words;
+  int* scr = reinterpret_cast<int*>(filled + words);            // 128 ints of scan scratch
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint8_t* gm = mask + (size_t)n * hw;
+  // ---- A: mask -> shared, parent = start of the pixel's row run (warp per row, ballot per 32 columns)
+  for (int y = wid; y < h; y += CCL_IMG_THREADS / 32) {
+    int carry_cls = 3, carry_start = 0;
+    for (int x0 = 0; x0 < w; x0 += 32) {
+      const int x = x0 + lane;
+      const bool in = x < w;
+      const int c = in ? (gm[(size_t)y * w + x] != 0 ? 1 : 0) : 2;
+      const unsigned fgb = __ballot_sync(0xffffffffu, c == 1);
+      const unsigned inb = __ballot_sync(0xffffffffu, in);
+      const unsigned same = c == 1 ? fgb : (c == 0 ? (~fgb & inb) : ~inb);
+      const unsigned below = (~same) & ((1u << lane) - 1u);
+      const int start = below ? x0 + 32 - __clz(below) : (c == carry_cls ? carry_start : x0);
+      if (in) { m[y * w + x] = (uint8_t)c; par[y * w + x] = (uint16_t)(y * w + start); }
+      carry_cls = __shfl_sync(0xffffffffu, c, 31);
+      carry_start = __shfl_sync(0xffffffffu, start, 31);
+    }
+  }
+  for (int i = tid; i < words; i += CCL_IMG_THREADS) { outer[i] = 0u; filled[i] = 0u; }
+  __syncthreads();
+  // ---- B: vertical / diagonal links (foreground 8-connected, background 4-connected), one link per run overlap
+  for (int y = 1 + wid; y < h; y += CCL_IMG_THREADS / 32) {
+    for (int x = lane; x < w; x += 32) {
+      const int p = y * w + x;
+      const int c = m[p];
+      const bool hasW = x > 0, hasE = x < w - 1;
+      const bool N_ = m[p - w] == c;
+      if (c == 1) {
+        if (N_) {
+          if (!hasW || m[p - 1] != 1 || m[p - w - 1] != 1) uf16_union(par, p, p - w);
+        } else {
+          if (hasE && m[p - w + 1] == 1) uf16_union(par, p, p - w + 1);
+          if (hasW && m[p - w - 1] == 1) uf16_union(par, p, p - w - 1);
+        }
+      } else if (N_ && (!hasW || m[p - 1] != 0 || m[p - w - 1] != 0)) {
+        uf16_union(par, p, p - w);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- C: full path compression
+  for (int i = tid; i < hw; i += CCL_IMG_THREADS) par[i] = (uint16_t)uf16_find_halve(par, i);
+  __syncthreads();
+  // ---- D: background sets that own an image-border pixel are connected to the outside
+  for (int i = tid; i < 2 * (w + h); i += CCL_IMG_THREADS) {
+    int y, x;
+    if (i < w) { y = 0; x = i; }
+    else if (i < 2 * w) { y = h - 1; x = i - w; }
+    else if (i < 2 * w + h) { y = i - 2 * w; x = 0; }
+    else { y = i - 2 * w - h; x = w - 1; }
+    const int p = y * w + x;
+    if (m[p] == 0) { const int r = par[p]; atomicOr(&outer[r >> 5], 1u << (r & 31)); }
+  }
+  __syncthreads();
+  // ---- E: 8-connectivity over filled pixels (foreground + holes); see ccl_merge2_kernel for the invariants
+  {
+    auto is_filled = [&](int q) -> bool {
+      if (m[q] != 0) return true;
+      const int r = *((volatile const uint16_t*)(par + q));
+      return ((outer[r >> 5] >> (r & 31)) & 1u) == 0u;
+    };
+    for (int y = wid; y < h; y += CCL_IMG_THREADS / 32) {
+      for (int x = lane; x < w; x += 32) {
+        const int p = y * w + x;
+        const bool fg = m[p] != 0;
+        if (!fg && !is_filled(p)) continue;
+        const bool hasW = x > 0, hasN = y > 0, hasE = x < w - 1;
+        auto link = [&](int q) { if (!(fg && m[q] != 0)) uf16_union(par, p, q); };
+        if (hasN && is_filled(p - w)) {
+          link(p - w);
+        } else {
+          if (hasN && hasE && is_filled(p - w + 1)) link(p - w + 1);
+          if (hasN && hasW && is_filled(p - w - 1)) link(p - w - 1);
+          else if (hasW && is_filled(p - 1)) link(p - 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- F: labels (root = first raster pixel of the filled component) -> global; filled bits
+  int* lab = labels + (size_t)n * hw;
+  for (int i0 = 0; i0 < hw; i0 += CCL_IMG_THREADS) {
+    const int i = i0 + tid;
+    bool f = false;
+    int root = -1;
+    if (i < hw) {
+      const int pr = par[i];
+      f = m[i] != 0 || ((outer[pr >> 5] >> (pr & 31)) & 1u) == 0u;      // an outer background pixel still points at its phase-1 root
+      if (f) root = uf16_find_halve(par, i);
+      lab[i] = root;
+    }
+    const unsigned fb = __ballot_sync(0xffffffffu, f);
+    if (lane == 0 && i0 + wid * 32 < hw) filled[(i0 >> 5) + wid] = fb;
+    if (f) par[i] = (uint16_t)root;       // compression while others still walk through i is safe: parents only move rootwards
+  }
+  __syncthreads();
+  // ---- G: rank the roots in raster order -> slot_of[root], records; thread = one run of `chunk` consecutive pixels
+  int* so = slot_of + (size_t)n * hw;
+  CompRec* cr = comps + (size_t)n * max_comps;
+  const int chunk = (hw + CCL_IMG_THREADS - 1) / CCL_IMG_THREADS;       // <= 64
+  const int c0 = tid * chunk;
+  unsigned long long rootbits = 0ull;
+  for (int k = 0; k < chunk; ++k) {
+    const int j = (k + lane) % chunk;                                   // rotated start: conflict-free 16-bit reads
+    const int i = c0 + j;
+    if (i < hw && par[i] == i && ((filled[i >> 5] >> (i & 31)) & 1u)) rootbits |= 1ull << j;
+  }
+  const int cnt = __popcll(rootbits);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) scr[1 + wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int own = scr[1 + lane];
+    int v = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    scr[33 + lane] = v - own;
+    if (lane == 31) scr[0] = v;
+  }
+  __syncthreads();
+  const int n_roots = scr[0];
+  {
+    int slot = scr[33 + wid] + incl - cnt;
+    unsigned long long b = rootbits;
+    while (b) {
+      const int j = __ffsll((long long)b) - 1;
+      b &= b - 1;
+      const int i = c0 + j;
+      so[i] = slot;
+      if (slot < max_comps) {
+        CompRec r; r.label = i; r.xmin = w; r.ymin = h; r.xmax = -1; r.ymax = -1;
+        r.n_pixels = 0; r.n_filled = 0; r.q3 = 0; r.q4 = 0;
+        cr[slot] = r;
+        for (int c = 0; c < n_cls; ++c) cls_sums[((size_t)n * max_comps + slot) * n_cls + c] = 0ull;
+      }
+      ++slot;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- H: per-component reductions, one 2x2 window per thread (bottom-right pixel (y,x), y in [0,h], x in [0,w])
+  auto Lab = [&](int yy, int xx) -> int {
+    if (yy < 0 || yy >= h || xx < 0 || xx >= w) return -1;
+    const int q = yy * w + xx;
+    return ((filled[q >> 5] >> (q & 31)) & 1u) ? (int)par[q] : -1;
+  };
+  for (int y = wid; y <= h; y += CCL_IMG_THREADS / 32) {
+    for (int x0 = 0; x0 <= w; x0 += 32) {
+      const int x = x0 + lane;
+      int slot = -1, l00 = -1, q3 = 0, q4 = 0;
+      if (x <= w) {
+        const int a = Lab(y - 1, x - 1), b = Lab(y - 1, x), c = Lab(y, x - 1);
+        l00 = Lab(y, x);
+        const int cntw = (a >= 0) + (b >= 0) + (c >= 0) + (l00 >= 0);
+        const int any = max(max(a, b), max(c, l00));          // all non-negative ones are equal
+        if (any >= 0) slot = so[any];
+        q3 = cntw == 3; q4 = cntw == 4;
+      }
+      if (slot >= max_comps) slot = -1;                       // overflow: reported via n_comps > max_comps
+      const unsigned active = __ballot_sync(0xffffffffu, slot >= 0);
+      if (slot < 0) continue;
+      const unsigned grp = __match_any_sync(active, slot);
+      const int leader = __ffs(grp) - 1;
+      const bool own = l00 >= 0;
+      const int sq3 = __reduce_add_sync(grp, q3), sq4 = __reduce_add_sync(grp, q4);
+      const int sfill = __reduce_add_sync(grp, own ? 1 : 0);
+      const int spix = __reduce_add_sync(grp, (own && m[y * w + x] != 0) ? 1 : 0);
+      const int xmn = __reduce_min_sync(grp, own ? x : 0x7fffffff);
+      const int xmx = __reduce_max_sync(grp, own ? x : -1);
+      if (lane == leader) {
+        CompRec* r = cr + slot;
+        if (sq3) atomicAdd(&r->q3, sq3);
+        if (sq4) atomicAdd(&r->q4, sq4);
+        if (sfill) {
+          atomicAdd(&r->n_filled, sfill);
+          if (spix) atomicAdd(&r->n_pixels, spix);
+          atomicMin(&r->xmin, xmn); atomicMin(&r->ymin, y);
+          atomicMax(&r->xmax, xmx); atomicMax(&r->ymax, y);
+        }
+      }
+      if (n_cls > 0) {
+        float e[UBD_MAX_CLASSES];
+        float s = 1.f;
+        if (own) {
+          const float* lg = cls_logits + ((size_t)n * hw + y * w + x) * cls_stride;
+          float mx = lg[0];
+          for (int c = 1; c < n_cls; ++c) mx = fmaxf(mx, lg[c]);
+          s = 0.f;
+          for (int c = 0; c < n_cls; ++c) { e[c] = expf(lg[c] - mx); s += e[c]; }
+        }
+        for (int c = 0; c < n_cls; ++c) {
+          const unsigned fx = own ? (unsigned)(e[c] / s * 16777216.0f) : 0u;
+          const unsigned tot = __reduce_add_sync(grp, fx);
+          if (lane == leader && tot)
+            atomicAdd(&cls_sums[((size_t)n * max_comps + slot) * n_cls + c], (unsigned long long)tot);
+        }
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  // ---- I: kept components of this image (2*contourArea > min_area_x2, utils.py:55)
+  {
+    const int cntc = min(n_roots, max_comps);
+    int k = 0;
+    for (int s = tid; s < cntc; s += CCL_IMG_THREADS) {
+      const volatile CompRec* r = cr + s;
+      k += (2 * r->q4 + r->q3) > min_area_x2;
+    }
+    k = __reduce_add_sync(0xffffffffu, k);
+    if (lane == 0) scr[1 + wid] = k;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int i = 0; i < CCL_IMG_THREADS / 32; ++i) t += scr[1 + i];
+      n_comps[n] = n_roots;
+      kept_count[n] = t;
+      atomicAdd(&totals->total_kept, t);
+      atomicMax(&totals->max_ncomp, n_roots);
+    }
+  }
+}

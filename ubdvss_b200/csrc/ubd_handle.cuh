@@ -59,6 +59,8 @@ struct ubd_handle_s {
   int opt_chunk = 0;              // images per L2-resident chunk (0 = auto)
   int opt_max_comps = 4096;       // component slots per image
   int opt_max_points = 0;         // hull candidate capacity (0 = auto)
+  int opt_fused_ccl = 0;          // 1: maps of <= 65,536 px are labelled by one CTA per image in shared memory (measured slower at batch 64:
+                                  // 0.79 vs 0.36 ms, 64 CTAs on 148 SMs and divergent pixel-level finds; profiles/r02_summary.md)
   int opt_gpu_boxes = 1;          // min-area rectangles on the GPU (0: hull candidates to the host, ubd_min_area_box)
 
   // inference workspaces
