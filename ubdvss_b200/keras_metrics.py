@@ -6,10 +6,9 @@ they are tokens: ``B200Model.compile`` records their order and ``train_on_batch`
 values from the pixel statistics ``ubd_metric_counts`` gathers on the GPU (confusion counts of the detection
 channel, class hits over object pixels) and from the loss components the loss kernels return.
 
-Deviation, on purpose: as METRICS the reference passes the raw ``y_true`` / ``y_pred`` tensors to
-``pixel_positive_loss`` & co. (losses.py:139-192), which expect prepared detection targets / probabilities, so
-Keras logs numbers that are not the loss components; the values reported here are the actual components of
-the loss that is being minimised."""
+The loss-component metrics (``pixel_positive_loss`` & co., losses.py:128-192) are wrapped by
+``@_prepare_detection_args`` in the reference, so Keras logs the very components of the loss that is being
+minimised; the values reported here are those components as the loss kernels return them."""
 from __future__ import annotations
 
 import numpy as np

@@ -74,12 +74,14 @@ class NetConfig:
         self._min_pixels_for_detection = min_pixels_for_detection
 
     def log_classification_mode(self):
+        """Called by train.py:97 before training; the wording is this package's own."""
+        names = self._class_names
         if self.is_classification_supported():
-            logging.info(f"Training classification with object types: {self._class_names}")
-        elif self._class_names is not None:
-            logging.info(f"Training WITHOUT classification, detection only for types: {self._class_names}")
+            logging.info("classification head enabled for %d object types: %s", len(names), names)
+        elif names is not None:
+            logging.info("detection only (class head disabled); object types of the dataset: %s", names)
         else:
-            logging.info("Training WITHOUT classification, detection for any barcode in datasets")
+            logging.info("detection only: any barcode of the datasets is a positive")
 
     def is_grey(self): return self._grey
     def get_scale(self): return self._scale
@@ -125,11 +127,8 @@ class NetConfig:
         self._class_name_to_id = dict((n, i) for i, n in enumerate(names))
 
     def __str__(self):
-        sb = ["Net Config:"]
-        for key in self.__dict__:
-            if key.startswith("_"):
-                sb.append("\t{key}={value}".format(key=key[1:], value=self.__dict__[key]))
-        return "\n".join(sb)
+        fields = {k.lstrip("_"): v for k, v in vars(self).items() if k.startswith("_") and k != "_class_name_to_id"}
+        return "NetConfig(" + ", ".join(f"{k}={v!r}" for k, v in sorted(fields.items())) + ")"
 
 
 class _ConfigUnpickler(pickle.Unpickler):
@@ -234,26 +233,67 @@ class B200Model:
     def count_params(self):
         return int(sum(int(np.prod(s)) for s in weight_shapes(self._cfg.is_grey(), self.n_classes)))
 
+    def _keras_layers(self, weights):
+        """``model.layers`` of net.py:286-313 with their weights, under the names Keras gives them in a fresh session:
+        the stride-2 layers are preceded by a ZeroPadding2D when ``fml_compatible`` (net.py:229-232)."""
+        names = ["input_1"]
+        fml = self._cfg.is_fml_compatible()
+        if fml:
+            names.append("zero_padding2d_1")
+        names += ["separable_conv2d_1", "separable_conv2d_2"]
+        if fml:
+            names.append("zero_padding2d_2")
+        names += ["separable_conv2d_3"] + [f"conv2d_{i}" for i in range(1, 8)]
+        by_layer = {}
+        for n, w in zip(_KERAS_NAMES, weights):
+            by_layer.setdefault(n.split("/")[0], []).append((n + ":0", w))
+        return [(n, by_layer.get(n, [])) for n in names]
+
     def save_weights(self, filepath, overwrite=True):
-        """Keras writes HDF5; h5py is absent here, so the same arrays go into an ``.npz`` keyed by the
-        Keras weight names, in ``get_weights()`` order (reading real ``.h5`` files: SURVEY 8f N3)."""
+        """``model.save_weights`` (net.py:423): a Keras HDF5 weight file (``hdf5.write_keras_weights``; h5py is not
+        needed) for ``.h5`` / ``.hdf5`` paths, else an ``.npz`` keyed by the Keras weight names in ``get_weights()`` order."""
         if not overwrite and os.path.exists(filepath):
             raise IOError(f"{filepath} exists")
+        if str(filepath).endswith((".h5", ".hdf5", ".keras.h5")):
+            from . import hdf5
+            hdf5.write_keras_weights(filepath, self._keras_layers(self.get_weights()))
+            return
         arrays = {f"{i:02d}:{n}": w for i, (n, w) in enumerate(zip(_KERAS_NAMES, self.get_weights()))}
         with open(filepath, "wb") as f:
             np.savez(f, **arrays)
 
     def load_weights(self, filepath, by_name=False):
+        """``model.load_weights`` / the weight part of ``keras.models.load_model`` (net.py:424, 477): reads the
+        HDF5 files Keras writes (weights-only or full ``model.save`` files) as well as this class's ``.npz``."""
         with open(filepath, "rb") as f:
             magic = f.read(8)
         if magic.startswith(b"\x89HDF"):
-            raise NotImplementedError("HDF5 weight files need h5py, which this environment lacks; "
-                                      "export with model.get_weights() + B200Model.set_weights")
+            from . import hdf5
+            arrays, names = hdf5.read_keras_weights(filepath)
+            if len(arrays) != len(_KERAS_NAMES):
+                raise ValueError(f"{filepath} holds {len(arrays)} weight arrays, this architecture has {len(_KERAS_NAMES)} "
+                                 "(net.py:286-313)")
+            self.set_weights(arrays)
+            return
         with np.load(filepath) as z:
             keys = sorted(z.files)
             self.set_weights([z[k] for k in keys])
 
     def save(self, filepath, overwrite=True, include_optimizer=True):
+        """``model.save`` (net.py:419-420, 427): weights under ``model_weights`` of a full-model HDF5 file.  The
+        ``model_config`` attribute names the architecture options only (Keras rebuilds the graph from its own JSON,
+        which this class does not emit), optimizer state is not stored: ``NetManager.load_model`` rebuilds the model
+        from ``config.pkl`` and loads the weights, which is all the reference's inference path needs."""
+        if not overwrite and os.path.exists(filepath):
+            raise IOError(f"{filepath} exists")
+        if str(filepath).endswith((".h5", ".hdf5")):
+            import json
+            from . import hdf5
+            cfg = json.dumps({"class_name": "Model", "config": {"name": self.name, "builder": "ubdvss_b200.net.B200Model",
+                                                                "grey": self._cfg.is_grey(), "fml_compatible": self._cfg.is_fml_compatible(),
+                                                                "n_classes": self.n_classes}})
+            hdf5.write_keras_weights(filepath, self._keras_layers(self.get_weights()), full_model=True, model_config=cfg)
+            return
         self.save_weights(filepath, overwrite)
 
     def summary(self, line_length=None, positions=None, print_fn=print):
@@ -347,14 +387,14 @@ class B200Model:
             out.append(float(parts[4]))
         return out
 
-    def test_on_batch(self, x, y, sample_weight=None):
-        logits = self.predict(x)
+    def test_on_batch(self, x, y, sample_weight=None, preprocessing=None):
+        logits = self.predict(x, preprocessing=preprocessing)
         parts, _ = self._engine.loss(logits, y)
         return self._batch_outputs(parts)
 
     def fit_generator(self, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None,
                       validation_data=None, validation_steps=None, max_queue_size=10, workers=0,
-                      use_multiprocessing=False, shuffle=True, initial_epoch=0, **kwargs):
+                      use_multiprocessing=False, shuffle=True, initial_epoch=0, preprocessing=None, **kwargs):
         """The loop ``train.py:176-188`` drives: ``steps_per_epoch`` x ``train_on_batch`` per epoch, then
         validation and ``on_epoch_end(epoch, logs)`` of every callback (callbacks read ``self.model``,
         keras_callbacks.py:77)."""
@@ -375,7 +415,7 @@ class B200Model:
             sums = np.zeros(len(self.metrics_names))
             for step in range(steps_per_epoch):
                 batch = next(generator)
-                vals = self.train_on_batch(batch[0], batch[1])
+                vals = self.train_on_batch(batch[0], batch[1], preprocessing=preprocessing)
                 sums += np.asarray(vals)
                 for cb in callbacks:
                     getattr(cb, "on_batch_end", lambda b, logs=None: None)(step, dict(zip(self.metrics_names, vals)))
@@ -384,7 +424,7 @@ class B200Model:
                 vs = np.zeros(len(self.metrics_names))
                 for _ in range(validation_steps):
                     vb = next(validation_data)
-                    vs += np.asarray(self.test_on_batch(vb[0], vb[1]))
+                    vs += np.asarray(self.test_on_batch(vb[0], vb[1], preprocessing=preprocessing))
                 logs.update({"val_" + k: v for k, v in zip(self.metrics_names, (vs / validation_steps).tolist())})
             for k, v in logs.items():
                 history.setdefault(k, []).append(v)
@@ -426,32 +466,55 @@ class NetManager:
     def get_keras_model(self):
         return self._model
 
-    def save_model(self):
+    def save_model(self, step=None):
+        """net.py:418-420: ``model{step:03d}.h5`` and ``model.h5`` (plus the config next to them)."""
+        os.makedirs(self._log_dir, exist_ok=True)
+        if step is not None:
+            self._model.save(os.path.join(self._log_dir, "model{:03d}.h5".format(step)))
         self._model.save(os.path.join(self._log_dir, self.CURRENT_MODEL_FILENAME))
         self.save_config()
 
     def save_inference(self):
-        """net.py:422-427: weights-only file, rebuilt model without optimizer state."""
-        self._model.save_weights(os.path.join(self._log_dir, self.MODEL_WEIGHTS_FILENAME))
+        """net.py:422-427: weights-only file, then the rebuilt model without optimizer state."""
+        os.makedirs(self._log_dir, exist_ok=True)
+        weights_path = os.path.join(self._log_dir, self.MODEL_WEIGHTS_FILENAME)
+        self._model.save_weights(weights_path)
+        self.build_model()
+        self._model.load_weights(weights_path)
         self._model.save(os.path.join(self._log_dir, self.INFERENCE_MODEL_FILENAME), include_optimizer=False)
         self.save_config()
 
-    def load_model(self, model_path=None):
-        """net.py:443-466: explicit path, else inference model, else current model."""
-        if model_path is None:
-            for name in (self.INFERENCE_MODEL_FILENAME, self.CURRENT_MODEL_FILENAME):
-                p = os.path.join(self._log_dir, name)
-                if os.path.exists(p):
-                    model_path = p
-                    break
-        assert model_path is not None and os.path.exists(model_path), f"Model {model_path} does not exist"
-        self.build_model()
-        self._model.load_weights(model_path)
+    def load_another_model(self, another_log_dir):
+        """net.py:429-441: take the model of another log dir (same architecture options); the options that do not
+        change the graph stay those of this manager.  Returns the merged config."""
+        other = NetManager(another_log_dir, self._net_config, device=self._device, precision=self._precision)
+        other.load_config()
+        other.load_model()
+        self._model = other._model
+        self._net_config = NetConfig.from_others(other._net_config, self._net_config.get_side_multiple(),
+                                                 self._net_config.get_max_side(), self._net_config.get_min_pixels_for_detection())
         return self._net_config
 
-    def load_weights_from(self, other_log_dir):
-        """net.py:429-441 (warm start from another log dir)."""
-        self._model.load_weights(os.path.join(other_log_dir, self.MODEL_WEIGHTS_FILENAME))
+    def load_model(self, path_to_model=None):
+        """net.py:443-466: ``inference_model.h5`` else ``model.h5`` of the log dir (or an explicit path, also relative
+        to the log dir); ``FileNotFoundError`` when neither exists.  Reads Keras HDF5 files (``hdf5.py``)."""
+        if path_to_model is not None:
+            if not os.path.exists(path_to_model):
+                path_to_model = os.path.join(self._log_dir, path_to_model)
+            return self._load_model(path_to_model)
+        candidates = [self.INFERENCE_MODEL_FILENAME, self.CURRENT_MODEL_FILENAME]
+        for fname in candidates:
+            p = os.path.join(self._log_dir, fname)
+            if os.path.exists(p):
+                return self._load_model(p)
+        raise FileNotFoundError(f"Model not found in dir {self._log_dir}. Must contain at least one of the following files {candidates}")
+
+    def _load_model(self, path_to_model):
+        assert os.path.exists(path_to_model), f"model fname does not exist, {path_to_model}"
+        logging.info(f"loading model from {path_to_model}")
+        self.build_model()
+        self._model.load_weights(path_to_model)
+        return self._net_config
 
     def save_config(self):
         os.makedirs(self._log_dir, exist_ok=True)
