@@ -401,6 +401,7 @@ static int ensure_maps(ubd_handle h, int n, int mh, int mw) {
 static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, int H, int W, int preproc,
                           float* d_logits, uint8_t* d_mask, float thr, const void* h_img = nullptr) {
   h->loss_pixels = 0;            // the handle's logits are about to be overwritten: ubd_metric_counts needs a new loss batch
+  h->last_logits = nullptr; h->last_ytrue = nullptr;
   HostTimer ht_fwd(h, 0);
   const int h4 = H / 4, w4 = W / 4;
   const int chunk = pick_chunk(h, n, H, W);
@@ -855,6 +856,7 @@ extern "C" int ubd_postprocess(ubd_handle h, const uint8_t* mask, const float* c
   if (n_cls < 0 || n_cls > UBD_MAX_CLASSES || (n_cls > 0 && !cls_logits)) UBD_FAIL(UBD_ERR_ARG, "bad class logits");
   UBD_CUDA(cudaSetDevice(h->device));
   const size_t q = (size_t)n * mh * mw;
+  h->loss_pixels = 0; h->last_logits = nullptr; h->last_ytrue = nullptr;      // d_logits is reused below
   ENSURE(h->d_mask, q);
   UBD_CUDA(cudaMemcpyAsync(h->d_mask.p, mask, q, cudaMemcpyHostToDevice, h->stream));
   if (n_cls > 0) {

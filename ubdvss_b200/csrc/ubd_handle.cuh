@@ -83,6 +83,8 @@ struct ubd_handle_s {
   bool have_grads = false;
   void* nccl_comm = nullptr;      // ncclComm_t of the data-parallel group (ubd_comm_init)
   int nccl_world = 0;
+  const float* last_logits = nullptr;   // logits / targets of that evaluation (may be the caller's device buffers)
+  const int* last_ytrue = nullptr;
   size_t loss_pixels = 0;         // pixels of the logits / targets of the last loss evaluation (ubd_metric_counts)
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 

@@ -65,7 +65,9 @@ loss_pixel_kernel(const float* __restrict__ logits, const int* __restrict__ y_tr
       for (int c = 2; c < n_out; ++c) mx = fmaxf(mx, lg[c]);
       float s = 0.f;
       for (int c = 1; c < n_out; ++c) s += expf(lg[c] - mx);
-      scls += (double)(logf(s) + mx - lg[yt]);       // label = yt - 1 -> channel yt
+      // label = yt - 1 -> channel yt; a label outside the class head gives NaN, as tf.nn.sparse_softmax_cross_entropy_with_logits
+      // does on the GPU (losses.py:78), instead of reading past the pixel's logits
+      scls += yt < n_out ? (double)(logf(s) + mx - lg[yt]) : (double)__int_as_float(0x7fc00000);
     }
   }
   npos = block_sum(npos, red); spos = block_sum(spos, red); sneg = block_sum(sneg, red); scls = block_sum(scls, red);
