@@ -140,6 +140,16 @@ int ubd_segment_submit_dev(ubd_handle h, const void* d_images, int in_dtype, int
                            int preproc, float logit_thr, int min_area_x2, int max_comps, int* ticket);
 int ubd_segment_wait(ubd_handle h, int ticket, ubd_component* comps_out, int max_comps, int32_t* n_comps_per_image);
 
+/* Input side (segmap_manager.py:136-167, data_generators.py:176-177): what the reference does to a decoded 8-bit image
+ * before the network - ``image.resize((out_w, out_h), Image.BICUBIC)`` then ``image.convert('L')`` when the net is grey -
+ * on the GPU, bit-identical to Pillow (fixed-point separable resampling with antialiasing, luma weights 19595/38470/7471).
+ * images: (n, h, w, c) uint8, c = 1 or 3; out: (n, out_h, out_w, 1 if to_grey and c == 3 else c).  The _dev form takes
+ * and leaves device buffers, so its output can be handed to ubd_segment_dev / ubd_segment_submit_dev directly. */
+int ubd_prepare_images(ubd_handle h, const uint8_t* images, int n, int height, int width, int channels,
+                       int out_height, int out_width, int to_grey, uint8_t* out);
+int ubd_prepare_images_dev(ubd_handle h, const uint8_t* d_images, int n, int height, int width, int channels,
+                           int out_height, int out_width, int to_grey, uint8_t* d_out);
+
 /* Pure host helper, usable without a GPU: cv2.boxPoints(cv2.minAreaRect(pts)) for one point set
  * (utils.py:56-57).  pts: n_pts (x,y) int32 pairs (any superset of the hull); box: 8 floats. */
 int ubd_min_area_box(const int32_t* pts_xy, int n_pts, float* box);

@@ -24,6 +24,24 @@ for native in (True, False):
     for _ in range(3):
         out = m.train_on_batch(x, y, preprocessing="mobilenet_like")
     res[native] = np.concatenate([a.ravel() for a in m.get_weights()])
+# the exchanged gradient of the CUDA path against the oracle: mean over the ranks of the per-replica gradients
+m = B200Model(NetConfig(), device=local, weights=w0)
+m.compile(Adam(1e-3), loss=losses.get_loss(False))
+m.set_distributed(True, native=True)
+m._engine.train_step(x, y, 1)
+scale = m._allreduce_grads()
+g_mine = np.concatenate([a.ravel() for a in m._engine.get_grads()]) * scale
+if rank == 0:
+    from oracle import loss as L, net as onet
+    per = []
+    for r in range(world):
+        xr = onet.preprocess(synth.synth_images(4, 128, 192, seed=10 + r).astype(np.float64), "mobilenet_like").astype(np.float32)
+        yr = synth.synth_targets(4, 32, 48, 0, seed=10 + r)
+        per.append(np.concatenate([a.ravel() for a in L.train_step_torch(w0, xr, yr, False)[2]]))
+    g_ref = np.mean(per, axis=0)
+    gerr = float(np.abs(g_mine - g_ref).max() / np.abs(g_ref).max())
+    print(f"all-reduced gradient vs oracle mean of per-replica gradients: rel err {gerr:.3e}")
+    assert gerr <= 2e-3
 diff = float(np.abs(res[True] - res[False]).max())
 t = torch.from_numpy(res[True]).cuda()
 lo, hi = t.clone(), t.clone()

@@ -54,6 +54,8 @@ SIGNATURES = {
     "ubd_segment_submit": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, C.POINTER(C.c_int)]),
     "ubd_segment_submit_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, C.POINTER(C.c_int)]),
     "ubd_segment_wait": (_i, [_vp, _i, _vp, _i, _vp]),
+    "ubd_prepare_images": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ubd_prepare_images_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ubd_min_area_box": (_i, [_vp, _i, _vp]),
     "ubd_train_step": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ubd_train_step_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

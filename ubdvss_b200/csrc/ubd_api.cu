@@ -12,6 +12,7 @@
 
 #include <dlfcn.h>
 #include "ubd_ccl.cuh"
+#include "ubd_prep.cuh"
 #include "ubd_common.cuh"
 #include "ubd_fp32.cuh"
 #include "ubd_handle.cuh"
@@ -865,6 +866,130 @@ extern "C" int ubd_postprocess(ubd_handle h, const uint8_t* mask, const float* c
   }
   return ccl_device(h, (uint8_t*)h->d_mask.p, n_cls ? (float*)h->d_logits.p : nullptr, n_cls, n_cls, n, mh, mw,
                     min_area_x2, labels_out, comps_out, max_comps, n_comps_per_image);
+}
+
+// ------------------------------------------------------------------------------------------------
+// input side: Pillow-exact bicubic resize + convert('L') on the GPU
+// ------------------------------------------------------------------------------------------------
+
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc (src/libImaging/Resample.c) for the bicubic filter.
+static int prep_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk) {
+  auto bicubic = [](double x) -> double {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+  };
+  const double scale = (double)in_size / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  bounds.assign(2 * (size_t)out_size, 0);
+  kk.assign((size_t)out_size * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    const double ss = 1.0 / filterscale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = bicubic((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < xmax; ++x) {
+      const double v = k[x] * (1 << 22);
+      kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v) : (int)(0.5 + v);
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+
+static int prepare_common(ubd_handle h, const uint8_t* d_src, int n, int H, int W, int C, int out_h, int out_w, int to_grey,
+                          uint8_t* d_dst) {
+  const bool need_h = out_w != W, need_v = out_h != H, grey = to_grey && C == 3;
+  const int Co = grey ? 1 : C;
+  std::vector<int> bx, kx, by, ky;
+  int ksx = 0, ksy = 0;
+  if (need_h) ksx = prep_coeffs(W, out_w, bx, kx);
+  if (need_v) ksy = prep_coeffs(H, out_h, by, ky);
+  const size_t tab = (bx.size() + kx.size() + by.size() + ky.size()) * sizeof(int);
+  ENSURE(h->prep_tab, std::max<size_t>(tab, 16));
+  int* t = (int*)h->prep_tab.p;
+  std::vector<int> all;
+  all.insert(all.end(), bx.begin(), bx.end()); all.insert(all.end(), kx.begin(), kx.end());
+  all.insert(all.end(), by.begin(), by.end()); all.insert(all.end(), ky.begin(), ky.end());
+  if (!all.empty()) {
+    UBD_CUDA(cudaMemcpyAsync(t, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    UBD_CUDA(cudaStreamSynchronize(h->stream));                    // `all` is a local
+  }
+  PrepAxis ax{t, t + bx.size(), ksx};
+  PrepAxis ay{t + bx.size() + kx.size(), t + bx.size() + kx.size() + by.size(), ksy};
+  // passes: horizontal (if the width changes), vertical (if the height changes), luma; intermediates in prep_a / prep_b
+  const size_t sz_h = (size_t)n * H * out_w * C, sz_v = (size_t)n * out_h * out_w * C;
+  const uint8_t* cur = d_src;
+  auto blocks = [&](size_t total) { return (unsigned)std::min<size_t>((total + 255) / 256, (size_t)h->n_sm * 16); };
+  if (need_h) {
+    uint8_t* dst = d_dst;
+    if (need_v || grey) { ENSURE(h->prep_a, sz_h); dst = (uint8_t*)h->prep_a.p; }
+    prep_resize_h_kernel<<<blocks(sz_h), 256, 0, h->stream>>>(cur, dst, ax, n, H, W, out_w, C); LAUNCH_CHECK();
+    cur = dst;
+  }
+  if (need_v) {
+    uint8_t* dst = d_dst;
+    if (grey) { ENSURE(h->prep_b, sz_v); dst = (uint8_t*)h->prep_b.p; }
+    prep_resize_v_kernel<<<blocks(sz_v), 256, 0, h->stream>>>(cur, dst, ay, n, H, out_h, out_w, C); LAUNCH_CHECK();
+    cur = dst;
+  }
+  if (grey) {
+    const size_t npx = (size_t)n * out_h * out_w;
+    prep_rgb2l_kernel<<<blocks(npx), 256, 0, h->stream>>>(cur, d_dst, npx); LAUNCH_CHECK();
+  } else if (cur == d_src) {
+    UBD_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)n * out_h * out_w * Co, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return UBD_OK;
+}
+
+static int check_prepare_args(ubd_handle h, const void* images, void* out, int n, int H, int W, int C, int out_h, int out_w) {
+  if (!images || !out) UBD_FAIL(UBD_ERR_ARG, "NULL argument");
+  if (n < 1 || H < 1 || W < 1 || out_h < 1 || out_w < 1 || (C != 1 && C != 3)) UBD_FAIL(UBD_ERR_ARG, "bad image shape (channels must be 1 or 3)");
+  return UBD_OK;
+}
+
+extern "C" int ubd_prepare_images_dev(ubd_handle h, const uint8_t* d_images, int n, int H, int W, int C, int out_h, int out_w,
+                                      int to_grey, uint8_t* d_out) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_prepare_args(h, d_images, d_out, n, H, W, C, out_h, out_w);
+  if (rc) return rc;
+  UBD_CUDA(cudaSetDevice(h->device));
+  return prepare_common(h, d_images, n, H, W, C, out_h, out_w, to_grey, d_out);
+}
+
+extern "C" int ubd_prepare_images(ubd_handle h, const uint8_t* images, int n, int H, int W, int C, int out_h, int out_w,
+                                  int to_grey, uint8_t* out) {
+  if (!h) return UBD_ERR_ARG;
+  int rc = check_prepare_args(h, images, out, n, H, W, C, out_h, out_w);
+  if (rc) return rc;
+  UBD_CUDA(cudaSetDevice(h->device));
+  const size_t ib = (size_t)n * H * W * C, ob = (size_t)n * out_h * out_w * ((to_grey && C == 3) ? 1 : C);
+  ENSURE(h->prep_in, ib);
+  ENSURE(h->prep_out, ob);
+  UBD_CUDA(cudaMemcpyAsync(h->prep_in.p, images, ib, cudaMemcpyHostToDevice, h->stream));
+  rc = prepare_common(h, (const uint8_t*)h->prep_in.p, n, H, W, C, out_h, out_w, to_grey, (uint8_t*)h->prep_out.p);
+  if (rc) return rc;
+  UBD_CUDA(cudaMemcpyAsync(out, h->prep_out.p, ob, cudaMemcpyDeviceToHost, h->stream));
+  UBD_CUDA(cudaStreamSynchronize(h->stream));
+  return UBD_OK;
 }
 
 // Test hook: one dilated layer (0..5, its own weights and dilation) on an NHWC 24-channel host map,

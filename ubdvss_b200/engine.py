@@ -240,6 +240,18 @@ class Engine:
                                                  C.c_void_p(d_logits_ptr or 0), ptr(comps), cap, ptr(counts)))
         return comps[:int(counts.sum())], counts
 
+    # ---------------------------------------------------------------- input side
+    def prepare_images(self, images, out_h: int, out_w: int, to_grey: bool = True):
+        """(N,H,W,1|3) uint8 -> (N,out_h,out_w,1|3) uint8: ``Image.resize((out_w, out_h), Image.BICUBIC)`` then
+        ``convert('L')`` (if ``to_grey`` and the input is RGB), bit-identical to Pillow, on the GPU."""
+        x = np.ascontiguousarray(images, dtype=np.uint8)
+        if x.ndim != 4 or x.shape[3] not in (1, 3):
+            raise ValueError(f"images must be (N,H,W,1|3) uint8, got {x.shape}")
+        n, H, W, c = x.shape
+        out = np.empty((n, out_h, out_w, 1 if (to_grey and c == 3) else c), np.uint8)
+        check(self._h, self._lib.ubd_prepare_images(self._h, ptr(x), n, H, W, c, int(out_h), int(out_w), int(bool(to_grey)), ptr(out)))
+        return out
+
     # ---------------------------------------------------------------- pipelined inference (two batches in flight)
     def segment_submit(self, images, logit_thr: float, min_area_x2: int, preproc: int = _lib.PREPROC_NONE,
                        mask_out=None, logits_out=None, max_comps: int = 0, device_ptr: int = 0, shape=None, dtype=None):

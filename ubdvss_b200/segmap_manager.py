@@ -73,3 +73,32 @@ class SegmapManager:
             pts = np.array(m.bbox, dtype=np.float64).reshape(-1, 2) * np.array([[sx, sy]])
             scaled.append(m.create_same_markup(pts.reshape(-1)))
         return resized, scaled
+
+    @staticmethod
+    def prepare_batch(images, net_config, max_side=None, engine=None):
+        """The image half of ``prepare_image_and_target`` + ``BatchGenerator._prepare_image`` for a batch of decoded
+        images of ONE size (segmap_manager.py:136-167, data_generators.py:176-177) on the GPU: the size rule, the bicubic
+        resize and the grey conversion.  -> ``(batch (N,h,w,1|3) uint8, (xscale, yscale))`` with the scales
+        ``MetaInfo`` carries (original / rescaled size, data_generators.py:186-190)."""
+        from .utils import default_engine
+        x = np.asarray(images)
+        n, h, w, c = x.shape
+        new_w, new_h = SegmapManager.network_input_size(w, h, net_config, max_side)
+        out = (engine or default_engine()).prepare_images(x, new_h, new_w, to_grey=net_config.is_grey())
+        return out, (w / new_w, h / new_h)
+
+
+def group_batches_by_size(items, batch_size, yield_incomplete_batches=True):
+    """Size-grouped batching of ``BatchGenerator.generate`` (data_generators.py:135-160): the prepared images are
+    sorted by size, grouped by shape and cut into batches of ``batch_size``; an incomplete batch ends its group and is
+    skipped unless ``yield_incomplete_batches``.  Yields lists of arrays of one shape."""
+    import itertools
+    data = sorted(items, key=lambda a: a.size)
+    for _, group in itertools.groupby(data, key=lambda a: a.shape):
+        group = list(group)
+        i = 0
+        while len(group) - i > 0:
+            if not yield_incomplete_batches and len(group) - i < batch_size:
+                break
+            yield group[i:i + batch_size]
+            i += batch_size
