@@ -508,7 +508,13 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
   // boxes on the GPU unless the map is too tall for the per-warp shared-memory arrays (then: hull candidates + host)
   const size_t box_smem = ((size_t)12 * mh + 10) * sizeof(int);
   R.gpu_boxes = h->opt_gpu_boxes && box_smem <= 48 * 1024;
-  if (R.gpu_boxes) ENSURE(R.box_recs, (size_t)std::max(max_out, 1) * sizeof(BoxRec));
+  // row-extent arrays of the kept components: two ints per (component, row); every row holds at least one pixel of its
+  // component and components do not share pixels, so the total cannot exceed the pixel count
+  const int max_rows = (int)std::min<size_t>((size_t)n * npx, (size_t)1 << 28);
+  if (R.gpu_boxes) {
+    ENSURE(R.box_recs, (size_t)std::max(max_out, 1) * sizeof(BoxRec));
+    ENSURE(h->row_ext, (size_t)max_rows * 2 * sizeof(int));
+  }
   else ENSURE(R.hull_pts, (size_t)max_pts * sizeof(HullPt));
   const size_t hdr_ints = n + sizeof(CclTotals) / sizeof(int);
   if (R.h_hdr_cap < hdr_ints) {
@@ -560,11 +566,14 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
       ccl_count_kept_kernel<<<n, 256, 0, h->stream>>>(comps, d_ncomps, d_kept, d_tot, max_comps, min_area_x2); LAUNCH_CHECK();
     }
     ccl_compact_kernel<<<n, 256, 0, h->stream>>>(comps, cls_sums, n_cls, d_ncomps, d_kept, (OutRec*)R.out_recs.p,
-                                                 (int*)h->out_index.p, max_comps, max_out, min_area_x2); LAUNCH_CHECK();
+                                                 (int*)h->out_index.p, max_comps, max_out, min_area_x2,
+                                                 d_tot, R.gpu_boxes ? (int*)h->row_ext.p : nullptr, max_rows); LAUNCH_CHECK();
     if (R.gpu_boxes) {
       // hull + rotating calipers of every kept component on the GPU, one warp each
-      ccl_boxes_kernel<<<std::max(max_out, 1), 32, box_smem, h->stream>>>(labels, (const OutRec*)R.out_recs.p, d_tot, (BoxRec*)R.box_recs.p,
-                                                                          mh, mw, max_out); LAUNCH_CHECK();
+      ccl_extents_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (const OutRec*)R.out_recs.p,
+                                                          (int*)h->row_ext.p, mh, mw, max_comps); LAUNCH_CHECK();
+      ccl_boxes_kernel<<<std::max(max_out, 1), 32, box_smem, h->stream>>>((const int*)h->row_ext.p, (const OutRec*)R.out_recs.p, d_tot,
+                                                                          (BoxRec*)R.box_recs.p, mh, mw, max_out); LAUNCH_CHECK();
     } else {
       ccl_points_kernel<<<tgrid, tblock, 0, h->stream>>>(labels, slot_of, (int*)h->out_index.p, (HullPt*)R.hull_pts.p,
                                                          d_tot, mh, mw, max_comps, max_pts); LAUNCH_CHECK();

@@ -418,7 +418,8 @@ __global__ void __launch_bounds__(256)
 ccl_compact_kernel(const CompRec* __restrict__ comps, const unsigned long long* __restrict__ cls_sums,
                    int n_cls, const int* __restrict__ n_comps, const int* __restrict__ kept_count,
                    OutRec* __restrict__ out, int* __restrict__ out_index_of_slot,
-                   int max_comps, int max_out, int min_area_x2) {
+                   int max_comps, int max_out, int min_area_x2,
+                   CclTotals* __restrict__ totals, int* __restrict__ ext, int max_rows) {
   const int n = blockIdx.x;
   const int cnt = min(n_comps[n], max_comps);
   const CompRec* cr = comps + (size_t)n * max_comps;
@@ -464,6 +465,17 @@ ccl_compact_kernel(const CompRec* __restrict__ comps, const unsigned long long* 
             if (best < 0 || v > bv) { best = c; bv = v; }
           }
           o.class_id = best;
+          // rows of the component in the row-extent arrays (ccl_extents_kernel fills them, ccl_boxes_kernel reads them):
+          // ext[2r] = max(w-1-x) over the row's pixels (left end), ext[2r+1] = max(x) (right end), both start at -1
+          o.row_base = -1;
+          if (ext != nullptr) {
+            const int rows = r.ymax - r.ymin + 1;
+            const int rb = atomicAdd(&totals->total_rows, rows);
+            if (rb + rows <= max_rows) {
+              o.row_base = rb;
+              for (int k = 0; k < 2 * rows; ++k) ext[2 * (size_t)rb + k] = -1;
+            }
+          }
           out[oi] = o;
         } else {
           oi = -1;
@@ -529,12 +541,37 @@ ccl_points_kernel(const int* __restrict__ labels, const int* __restrict__ slot_o
 // adds the angle / corner trigonometry of cv2.boxPoints (libm), a few hundred nanoseconds per component.
 // ------------------------------------------------------------------------------------------------
 
+// Left / right end of every row of every kept component: one thread per pixel, only run ends touch memory.
+__global__ void __launch_bounds__(256)
+ccl_extents_kernel(const int* __restrict__ labels, const int* __restrict__ slot_of, const int* __restrict__ out_index_of_slot,
+                   const OutRec* __restrict__ recs, int* __restrict__ ext, int h, int w, int max_comps) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int* lab = labels + (size_t)n * h * w;
+  const int l = lab[y * w + x];
+  if (l < 0) return;
+  const bool le = x == 0 || lab[y * w + x - 1] != l;
+  const bool re = x == w - 1 || lab[y * w + x + 1] != l;
+  if (!le && !re) return;
+  const int slot = slot_of[(size_t)n * h * w + l];
+  if (slot >= max_comps) return;
+  const int comp = out_index_of_slot[(size_t)n * max_comps + slot];
+  if (comp < 0) return;
+  const OutRec& r = recs[comp];
+  if (r.row_base < 0) return;
+  int* e = ext + 2 * ((size_t)r.row_base + (y - r.ymin));
+  if (le) atomicMax(e, w - 1 - x);
+  if (re) atomicMax(e + 1, x);
+}
+
 __device__ __forceinline__ long long ccl_cross(int ox, int oy, int ax, int ay, int bx, int by) {
   return (long long)(ax - ox) * (by - oy) - (long long)(ay - oy) * (bx - ox);
 }
 
 __global__ void __launch_bounds__(32)
-ccl_boxes_kernel(const int* __restrict__ labels, const OutRec* __restrict__ recs, const CclTotals* __restrict__ totals,
+ccl_boxes_kernel(const int* __restrict__ ext, const OutRec* __restrict__ recs, const CclTotals* __restrict__ totals,
                  BoxRec* __restrict__ boxes, int h, int w, int max_out) {
   extern __shared__ int box_smem[];
   const int comp = blockIdx.x, lane = threadIdx.x;
@@ -548,21 +585,13 @@ ccl_boxes_kernel(const int* __restrict__ labels, const OutRec* __restrict__ recs
   float* vx = reinterpret_cast<float*>(hy + 2 * h + 2);
   float* vy = vx + 2 * h + 2;
   float* inv = vy + 2 * h + 2;
-  const int* lab = labels + (size_t)r.image * h * w;
-  // (1) row extents
-  for (int y = r.ymin; y <= r.ymax; ++y) {
-    int lo = 0x7fffffff, hi = -1;
-    for (int x0 = r.xmin; x0 <= r.xmax; x0 += 32) {
-      const int x = x0 + lane;
-      const bool in = x <= r.xmax && lab[(size_t)y * w + x] == r.label;
-      const unsigned b = __ballot_sync(0xffffffffu, in);
-      if (b) {
-        if (lo == 0x7fffffff) lo = x0 + __ffs(b) - 1;
-        hi = x0 + 31 - __clz(b);
-      }
-    }
-    if (lane == 0) { L[y - r.ymin] = lo; R[y - r.ymin] = hi; }
+  if (r.row_base < 0) {                    // the row-extent arrays overflowed (reported by the host): leave a marker
+    if (lane == 0) { BoxRec o; o.cx = o.cy = o.w = o.h = o.ax = o.ay = 0.f; o.n_hull = -1; o.x0 = o.y0 = o.x1 = o.y1 = 0; boxes[comp] = o; }
+    return;
   }
+  // (1) row extents
+  const int* e = ext + 2 * (size_t)r.row_base;
+  for (int i = lane; i < rows; i += 32) { L[i] = w - 1 - e[2 * i]; R[i] = e[2 * i + 1]; }
   __syncwarp();
   if (lane != 0) return;
   // (2) hull.  Every row of an 8-connected filled component between ymin and ymax holds at least one pixel.

@@ -54,8 +54,9 @@ static inline WeightSpec make_weight_spec(int grey, int n_classes) {
 // Results of the connected-component stage as the host reads them back (ubd_ccl.cuh writes them).
 struct OutRec {
   int image, label, xmin, ymin, xmax, ymax, n_pixels, n_filled, area_x2, class_id, slot;
+  int row_base;                            // first entry of the component's rows in the row-extent arrays (GPU rectangles)
 };
-struct CclTotals { int total_kept, total_pts, max_ncomp, pad; };
+struct CclTotals { int total_kept, total_pts, max_ncomp, total_rows; };
 // min-area rectangle of a kept component as ccl_boxes_kernel leaves it (centre, size, first edge vector, hull size
 // and its first two points for the degenerate cases)
 struct BoxRec { float cx, cy, w, h, ax, ay; int n_hull, x0, y0, x1, y1; };

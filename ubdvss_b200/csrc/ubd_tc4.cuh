@@ -81,6 +81,14 @@ __device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
   return done;
 }
 
+// packed fp32x2 FMA (one issue slot for two lanes of work on sm_100)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+
 constexpr int PAD = UBD_MAP_PAD;
 constexpr int SEG = 128;
 constexpr int SW_MAX = 256;                               // strip = two segments
@@ -113,7 +121,7 @@ template <bool BF16> struct Smem {
   uint32_t tmem_base;
   int abort_flag;
   float lut[256];                // L1-producer variant: uint8 -> preprocessed float
-  float l1w[9 + UBD_NF + UBD_NF]; // dw1[9], pw1[24], b1[24] (grey input)
+  __align__(16) float l1w[12 + UBD_NF + UBD_NF]; // dw1[9] (+3 pad), pw1[24], b1[24] (grey input)
 };
 
 // A contiguous run of output rows inside one (image, strip, y-phase).
@@ -472,8 +480,8 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     const int t = (warp - 12) * L1_PXW + lane;              // staged pixel of this thread
     const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
     for (int i = tl; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
-    for (int i = tl; i < 9 + 2 * UBD_NF; i += L1_THREADS)
-      S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 9 + UBD_NF ? l1.pw1[i - 9] : l1.b1[i - 9 - UBD_NF]);
+    for (int i = tl; i < 12 + 2 * UBD_NF; i += L1_THREADS)
+      S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 12 ? 0.f : (i < 12 + UBD_NF ? l1.pw1[i - 12] : l1.b1[i - 12 - UBD_NF]));
     asm volatile("bar.sync 1, %0;" ::"n"(L1_THREADS) : "memory");   // the L1 warps only
     float dwr[9];
 #pragma unroll
@@ -546,9 +554,18 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
               for (int q = 0; q < 9; ++q)
                 if (valid & (1u << q)) a = fmaf(S.lut[b[q]], dwr[q], a);
             }
+            // pointwise 1 -> 24, bias, ReLU: packed fp32x2 FMAs on 16-byte weight loads (pw1 at l1w[12..36), b1 at l1w[36..60))
+            const float2 aa = make_float2(a, a);
+            const float4* pw4 = reinterpret_cast<const float4*>(S.l1w + 12);
+            const float4* b4 = reinterpret_cast<const float4*>(S.l1w + 12 + UBD_NF);
             float o[UBD_NF];
 #pragma unroll
-            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(fmaf(a, S.l1w[9 + c], S.l1w[9 + UBD_NF + c]), 0.f);
+            for (int g = 0; g < UBD_NG; ++g) {
+              const float4 pw = pw4[g], bb = b4[g];
+              const float2 lo = ffma2(aa, make_float2(pw.x, pw.y), make_float2(bb.x, bb.y));
+              const float2 hi = ffma2(aa, make_float2(pw.z, pw.w), make_float2(bb.z, bb.w));
+              o[4 * g] = fmaxf(lo.x, 0.f); o[4 * g + 1] = fmaxf(lo.y, 0.f); o[4 * g + 2] = fmaxf(hi.x, 0.f); o[4 * g + 3] = fmaxf(hi.y, 0.f);
+            }
             if constexpr (BF16) {
 #pragma unroll
               for (int g = 0; g < 3; ++g)
