@@ -285,7 +285,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     eng = Engine(device=local_rank, precision=precision, n_classes=n_classes)
     eng.set_weights(weights)
-    for opt in ("tc_variant", "dense_l2", "stem_chunk", "stem_variant", "chunk"):
+    for opt in ("tc_variant", "dense_l2", "stem_chunk", "stem_variant", "chunk", "fused_ccl", "gpu_boxes", "pipeline", "pipe_ring"):
         if os.environ.get("UBD_" + opt.upper()):
             eng.set_option(opt, int(os.environ["UBD_" + opt.upper()]))
     # two different batches alternate, so that nothing of step k is still in L2 for step k+1

@@ -84,16 +84,24 @@ def test_gpu_rectangles_equal_host_rectangles(shape):
 
 
 @pytest.mark.parametrize("shape", [(12, 40, 56), (6, 256, 256), (3, 17, 33), (2, 1, 70), (2, 50, 1), (1, 128, 512)])
-def test_whole_image_kernel_bit_exact(shape):
-    """Option fused_ccl 1: maps of up to 65,536 px are labelled by one CTA per image in shared memory
-    (ccl_image_kernel); same labels, records and boxes as the default tiled multi-kernel path."""
+@pytest.mark.parametrize("variant", [1, 2])
+def test_whole_image_kernel_bit_exact(shape, variant):
+    """Option fused_ccl 1 / 2: maps of up to 65,536 px are labelled by one CTA per image in shared memory (pixel-level
+    ccl_image_kernel / run-length ccl_rle_kernel); same labels, records, class votes and boxes as the tiled path."""
     from ubdvss_b200.engine import Engine
     e = Engine()
     e.set_option("fused_ccl", 0)
     masks = synth.stress_masks(*shape, seed=sum(shape))
     comps_t, counts_t = _check_against_spec(e, masks)
-    e.set_option("fused_ccl", 1)
+    e.set_option("fused_ccl", variant)
     comps_f, counts_f = _check_against_spec(e, masks)
+    assert np.array_equal(counts_t, counts_f) and np.array_equal(comps_t, comps_f)
+    cls = np.random.default_rng(1).normal(0, 2, size=masks.shape + (5,)).astype(np.float32)
+    e.set_option("fused_ccl", 0)
+    _, ct, nt = e.postprocess(masks, cls, 10)
+    e.set_option("fused_ccl", variant)
+    _, cf, nf = e.postprocess(masks, cls, 10)
+    assert np.array_equal(nt, nf) and np.array_equal(ct, cf)
     assert np.array_equal(counts_t, counts_f) and np.array_equal(comps_t, comps_f)
 
 

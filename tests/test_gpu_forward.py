@@ -229,3 +229,25 @@ def test_benchmark_batch_against_oracle(precision, n_classes):
                 assert int(c["class_id"]) == k
     # identical images of the batch give identical results wherever they sit in the launch
     assert np.array_equal(logits[0], logits[8]) and np.array_equal(mask[n - 8], mask[n - 16])
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("n,hw", [(32, (64, 128)), (26, (256, 192)), (40, (128, 1088))])
+def test_layer_pipelined_launch_is_bit_identical(precision, n, hw):
+    """Chunks of >= 24 images run the six dilated layers as ONE layer-pipelined launch (CTA groups per layer, ring buffers
+    between the layers, option pipeline); the result must equal the launch-per-layer path bit for bit: small maps
+    (fewer rows than CTAs in a group), several strips per row (map wider than 256), ring depths 2 and 3, class head."""
+    for n_classes in (0, 3):
+        w = synth.synth_weights(n_classes, seed=3, calibrated=True)
+        eng = _engine(precision=precision, n_classes=n_classes)
+        eng.set_weights(w)
+        x = synth.synth_images(8, hw[0], hw[1], seed=n)
+        x = np.ascontiguousarray(np.concatenate([x] * (n // 8 + 1), 0)[:n])
+        eng.set_option("pipeline", 0)
+        ref = eng.forward(x, _lib.PREPROC_MOBILENET)
+        for ring in (2, 3):
+            eng.set_option("pipeline", 1)
+            eng.set_option("pipe_ring", ring)
+            got = eng.forward(x, _lib.PREPROC_MOBILENET)
+            assert np.array_equal(got, ref), (ring, float(np.abs(got - ref).max()))
+        assert np.array_equal(ref[0], ref[8])

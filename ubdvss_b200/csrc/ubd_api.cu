@@ -141,6 +141,7 @@ extern "C" int ubd_create(int device, int grey, int fml_compatible, int n_classe
   stem_setup_attributes();
   stemf_setup_attributes();
   cudaFuncSetAttribute(ccl_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_image_smem(CCL_IMG_MAX_PX));
+  cudaFuncSetAttribute(ccl_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   *out = h;
   return UBD_OK;
 }
@@ -215,8 +216,10 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   else if (!strcmp(name, "dense_l2")) h->opt_dense_l2 = value != 0;
   else if (!strcmp(name, "stem_variant")) h->opt_stem_variant = (int)value;
   else if (!strcmp(name, "gpu_boxes")) h->opt_gpu_boxes = value != 0;
-  else if (!strcmp(name, "fused_ccl")) h->opt_fused_ccl = value != 0;
+  else if (!strcmp(name, "fused_ccl")) h->opt_fused_ccl = (int)value;
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
+  else if (!strcmp(name, "pipeline")) h->opt_pipeline = value != 0;
+  else if (!strcmp(name, "pipe_ring")) { if (value < 2) UBD_FAIL(UBD_ERR_ARG, "pipe_ring must be >= 2"); h->opt_pipe_ring = (int)value; }
   else if (!strcmp(name, "stem_chunk")) h->opt_stem_chunk = (int)value;
   else if (!strcmp(name, "tc_trace")) {
     if (value) { ENSURE(h->tc_trace, 8 * 1024 * 4 * sizeof(long long)); UBD_CUDA(cudaMemset(h->tc_trace.p, 0, h->tc_trace.cap)); }
@@ -449,7 +452,17 @@ static int forward_device(ubd_handle h, const void* d_img, int in_dtype, int n, 
       else rc = run_stem(h, img, in_dtype, preproc, sn, H, W, (float4*)h->act1.p, (float4*)h->act2.p, a3);
       if (rc) return rc;
     }
-    // ---- dilated layers and head over the whole chunk
+    // ---- dilated layers and head over the whole chunk: one launch per layer, or (option "pipeline") one layer-pipelined
+    //      launch whose inter-layer maps stay in L2 rings
+    if (h->precision != UBD_FP32 && h->opt_pipeline && h->opt_tc_variant && cn >= 4 * UBD_NLAYERS_DIL && h->n_sm >= 4 * UBD_NLAYERS_DIL) {
+      ProfScope ps(h, &h->prof_dil);
+      tc::HeadArgs ha{h->d_params + h->spec.off[21], h->d_params + h->spec.off[22], h->spec.n_out, thr,
+                      d_logits ? d_logits + (size_t)c0 * q_px * h->spec.n_out : nullptr,
+                      d_mask ? d_mask + (size_t)c0 * q_px : nullptr};
+      rc = tc4_launch_pipeline(h, A, cn, h4, w4, &ha);
+      if (rc) return rc;
+      continue;
+    }
     for (int l = 0; l < UBD_NLAYERS_DIL; ++l) {
       ProfScope ps(h, &h->prof_dil);
       const float* w = h->d_params + h->spec.off[9 + 2 * l];
@@ -493,7 +506,10 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
   const size_t pstride = (npx + 1 + 31) & ~(size_t)31;
   const int max_comps = h->opt_max_comps;
   const int max_pts = h->opt_max_points > 0 ? h->opt_max_points : (int)std::min<size_t>((size_t)n * npx / 2 + 1024, (size_t)1 << 26);
-  const bool fused = h->opt_fused_ccl && npx <= (size_t)CCL_IMG_MAX_PX;
+  // whole-image kernels (one CTA per image, shared memory): 2 = run-length variant, 1 = pixel variant; else the tiled path
+  const bool rle = h->opt_fused_ccl == 2 && npx <= (size_t)CCL_IMG_MAX_PX && ccl_rle_smem(mh, mw) <= (size_t)227 * 1024;
+  const bool fused = rle || (h->opt_fused_ccl == 1 && npx <= (size_t)CCL_IMG_MAX_PX);
+  if (rle) ENSURE(h->run_label, (size_t)n * npx * 2 * sizeof(int));
   if (!fused) {
     ENSURE(h->parent, (size_t)n * pstride * sizeof(int));
     ENSURE(h->outer, (size_t)n * pstride);
@@ -541,7 +557,11 @@ static int ccl_enqueue(ubd_handle h, int s, const uint8_t* d_mask, const float* 
     HostTimer ht_enq(h, 1);
     ProfScope ps_ccl(h, &h->prof_ccl);
     UBD_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(CclTotals), h->stream));
-    if (fused) {
+    if (rle) {
+      ccl_rle_kernel<<<n, CCL_IMG_THREADS, ccl_rle_smem(mh, mw), h->stream>>>(d_mask, labels, slot_of, (int*)h->run_label.p, comps, d_cls, cls_stride,
+                                                                             cls_sums, n_cls, d_ncomps, d_kept, d_tot, mh, mw, max_comps, min_area_x2);
+      LAUNCH_CHECK();
+    } else if (fused) {
       // one CTA per image, everything in shared memory (ubd_ccl.cuh, "whole-image variant")
       ccl_image_kernel<<<n, CCL_IMG_THREADS, ccl_image_smem((int)npx), h->stream>>>(d_mask, labels, slot_of, comps, d_cls, cls_stride, cls_sums, n_cls,
                                                                                    d_ncomps, d_kept, d_tot, mh, mw, max_comps, min_area_x2);

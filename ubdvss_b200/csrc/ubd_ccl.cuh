@@ -1004,3 +1004,334 @@ ccl_image_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels, int
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Run-length variant of the whole-image kernel ("rle"): the same algorithm on ROW RUNS instead of pixels.
+// A row is a few 32-bit words of foreground bits; a run = maximal interval of one class (foreground or
+// background) in a row, identified by its rank in raster order: run id of pixel (y,x) = (number of run starts before
+// its word) + popc(start bits of the word up to x) - 1, so runs need no table of their own - only a 16-bit parent
+// per run (at most h*w <= 65,536 runs).  Links between rows are found with bit operations on the words (a run
+// touches the runs above it whose bits intersect its window, widened by one pixel for 8-connectivity); the
+// filled mask, the bit-quad counts of 2*contourArea and the per-run pixel counts are popcounts.  One CTA per
+// image, every pass separated by __syncthreads; typical masks have a few thousand runs, so a pass is a handful
+// of iterations per thread.
+// ------------------------------------------------------------------------------------------------
+static inline size_t ccl_rle_smem(int h, int w) {
+  const size_t nw = (size_t)h * ((w + 31) / 32), hw = (size_t)h * w;
+  return 3 * nw * 4 + ((nw + 1) * 2 + 15 & ~(size_t)15) + ((hw + 31) / 32) * 4 + ((hw * 2 + 15) & ~(size_t)15) + 1024;
+}
+
+__global__ void __launch_bounds__(CCL_IMG_THREADS, 1)
+ccl_rle_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels, int* __restrict__ slot_of, int* __restrict__ run_label,
+               CompRec* __restrict__ comps, const float* __restrict__ cls_logits, int cls_stride,
+               unsigned long long* __restrict__ cls_sums, int n_cls, int* __restrict__ n_comps,
+               int* __restrict__ kept_count, CclTotals* __restrict__ totals, int h, int w, int max_comps, int min_area_x2) {
+  extern __shared__ __align__(16) uint8_t ccl_smem[];
+  const int hw = h * w, WPR = (w + 31) >> 5, NW = h * WPR;
+  unsigned* F = reinterpret_cast<unsigned*>(ccl_smem);            // foreground bits
+  unsigned* X = F + NW;                                           // filled bits (foreground + holes)
+  unsigned* S = X + NW;                                           // run-start bits
+  uint16_t* WB = reinterpret_cast<uint16_t*>(S + NW);             // runs that start before the word (raster order)
+  unsigned* outer = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(WB) + (((size_t)(NW + 1) * 2 + 15) & ~(size_t)15));
+  uint16_t* par = reinterpret_cast<uint16_t*>(outer + ((hw + 31) >> 5));
+  int* scr = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(par) + (((size_t)hw * 2 + 15) & ~(size_t)15));   // 256 ints
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NWARP = CCL_IMG_THREADS / 32;
+  const uint8_t* gm = mask + (size_t)n * hw;
+  const unsigned vlast = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xFFFFFFFFu;      // valid bits of a row's last word
+  auto valid = [&](int wd) -> unsigned { return wd == WPR - 1 ? vlast : 0xFFFFFFFFu; };
+  // run id of the pixel at bit `bit` of word `wi`
+  auto runid = [&](int wi, int bit) -> int { return (int)WB[wi] + __popc(S[wi] & (0xFFFFFFFFu >> (31 - bit))) - 1; };
+  // block-wide exclusive scan of one int per thread; returns the exclusive prefix, total in scr[0]
+  auto block_scan = [&](int v) -> int {
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                                              // scr is reused between scans
+    if (lane == 31) scr[1 + wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int own = scr[1 + lane];
+      int s = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+      scr[33 + lane] = s - own;
+      if (lane == 31) scr[0] = s;
+    }
+    __syncthreads();
+    return scr[33 + wid] + incl - v;
+  };
+
+  // ---- A: foreground words and run-start bits, one warp per row
+  for (int y = wid; y < h; y += NWARP) {
+    unsigned carry = 0u;
+    for (int wd = 0; wd < WPR; ++wd) {
+      const int x = wd * 32 + lane;
+      const bool fg = x < w && gm[(size_t)y * w + x] != 0;
+      const unsigned bits = __ballot_sync(0xffffffffu, fg);
+      if (lane == 0) {
+        const unsigned diff = (bits ^ ((bits << 1) | carry)) | (wd == 0 ? 1u : 0u);
+        F[y * WPR + wd] = bits;
+        S[y * WPR + wd] = diff & valid(wd);
+      }
+      carry = bits >> 31;
+    }
+  }
+  for (int i = tid; i < ((hw + 31) >> 5); i += CCL_IMG_THREADS) outer[i] = 0u;
+  __syncthreads();
+  // run-id bases: exclusive scan of the per-word start counts in raster order (thread = `chunk` consecutive words)
+  const int chunk = (NW + CCL_IMG_THREADS - 1) / CCL_IMG_THREADS;
+  int n_runs;
+  {
+    int c = 0;
+    for (int k = 0; k < chunk; ++k) { const int wi = tid * chunk + k; if (wi < NW) c += __popc(S[wi]); }
+    int base = block_scan(c);
+    n_runs = scr[0];
+    for (int k = 0; k < chunk; ++k) { const int wi = tid * chunk + k; if (wi < NW) { WB[wi] = (uint16_t)base; base += __popc(S[wi]); } }
+  }
+  for (int r = tid; r < n_runs; r += CCL_IMG_THREADS) par[r] = (uint16_t)r;
+  __syncthreads();
+  // contiguous run of set bits of m that starts at its lowest set bit
+  auto low_run = [](unsigned m) -> unsigned { return m & ~(m + (m & (0u - m))); };
+
+  // ---- B: links to the row above: foreground 8-connected, background 4-connected
+  for (int wi = WPR + tid; wi < NW; wi += CCL_IMG_THREADS) {
+    const int wd = wi % WPR, up = wi - WPR;
+    const unsigned v = valid(wd);
+    const unsigned cur = F[wi], above = F[up];
+    unsigned m = cur & v;
+    while (m) {                                                   // foreground pieces of this word
+      const unsigned rm = low_run(m);
+      m &= ~rm;
+      const int a = __ffs(rm) - 1, b = 31 - __clz(rm);
+      const int r = runid(wi, a);
+      unsigned t = above & (rm | (rm << 1) | (rm >> 1));
+      while (t) { const unsigned seg = low_run(t); t &= ~seg; uf16_union(par, r, runid(up, __ffs(seg) - 1)); }
+      if (a == 0 && wd > 0 && (F[up - 1] >> 31)) uf16_union(par, r, runid(up - 1, 31));
+      if (b == 31 && wd + 1 < WPR && (F[up + 1] & 1u)) uf16_union(par, r, runid(up + 1, 0));
+    }
+    m = ~cur & v;
+    while (m) {                                                   // background pieces
+      const unsigned rm = low_run(m);
+      m &= ~rm;
+      const int r = runid(wi, __ffs(rm) - 1);
+      unsigned t = ~above & rm;
+      while (t) { const unsigned seg = low_run(t); t &= ~seg; uf16_union(par, r, runid(up, __ffs(seg) - 1)); }
+    }
+  }
+  __syncthreads();
+  // ---- C: flatten
+  for (int r = tid; r < n_runs; r += CCL_IMG_THREADS) par[r] = (uint16_t)uf16_find_halve(par, r);
+  __syncthreads();
+  // ---- D: background sets that own an image-border pixel are connected to the outside
+  {
+    auto mark = [&](int r) { const int root = par[r]; atomicOr(&outer[root >> 5], 1u << (root & 31)); };
+    for (int i = tid; i < 2 * WPR; i += CCL_IMG_THREADS) {        // first and last row: every background piece
+      const int wd = i % WPR, wi = (i < WPR ? 0 : (h - 1) * WPR) + wd;
+      unsigned m = ~F[wi] & valid(wd);
+      while (m) { const unsigned rm = low_run(m); m &= ~rm; mark(runid(wi, __ffs(rm) - 1)); }
+    }
+    for (int y = tid; y < h; y += CCL_IMG_THREADS) {              // first and last pixel of every row
+      if (!(F[y * WPR] & 1u)) mark(runid(y * WPR, 0));
+      const int lw = y * WPR + WPR - 1, lb = (w - 1) & 31;
+      if (!((F[lw] >> lb) & 1u)) mark(runid(lw, lb));
+    }
+  }
+  __syncthreads();
+  // ---- E0: filled bits = foreground + background runs whose set is not outer
+  for (int wi = tid; wi < NW; wi += CCL_IMG_THREADS) {
+    const unsigned cur = F[wi];
+    unsigned x = cur, m = ~cur & valid(wi % WPR);
+    while (m) {
+      const unsigned rm = low_run(m);
+      m &= ~rm;
+      const int root = par[runid(wi, __ffs(rm) - 1)];
+      if (!((outer[root >> 5] >> (root & 31)) & 1u)) x |= rm;
+    }
+    X[wi] = x;
+  }
+  __syncthreads();
+  // ---- E1: 8-connectivity over filled pixels: neighbouring runs of a row, then the row above
+  for (int wi = tid; wi < NW; wi += CCL_IMG_THREADS) {
+    const int wd = wi % WPR;
+    const unsigned xc = X[wi];
+    {   // a run that starts at column > 0 and its left neighbour, both filled
+      unsigned st = S[wi] & xc;
+      if (wd == 0) st &= ~1u;
+      const unsigned left = (xc << 1) | (wd > 0 ? (X[wi - 1] >> 31) : 0u);
+      st &= left;
+      while (st) { const int b = __ffs(st) - 1; st &= st - 1; const int r = runid(wi, b); uf16_union(par, r, r - 1); }
+    }
+    if (wi >= WPR) {
+      const int up = wi - WPR;
+      const unsigned xa = X[up];
+      unsigned m = xc;
+      while (m) {
+        const unsigned rm = low_run(m);
+        m &= ~rm;
+        const int a = __ffs(rm) - 1, b = 31 - __clz(rm);
+        const int r = runid(wi, a);
+        unsigned t = xa & (rm | (rm << 1) | (rm >> 1));
+        while (t) { const unsigned seg = low_run(t); t &= ~seg; uf16_union(par, r, runid(up, __ffs(seg) - 1)); }
+        if (a == 0 && wd > 0 && (X[up - 1] >> 31)) uf16_union(par, r, runid(up - 1, 31));
+        if (b == 31 && wd + 1 < WPR && (X[up + 1] & 1u)) uf16_union(par, r, runid(up + 1, 0));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- F: flatten
+  for (int r = tid; r < n_runs; r += CCL_IMG_THREADS) par[r] = (uint16_t)uf16_find_halve(par, r);
+  __syncthreads();
+  // ---- G: rank the root runs in raster order -> slot, label (= raster index of the run's first pixel), records
+  int* so = slot_of + (size_t)n * hw;                 // slot by LABEL (raster index of the first pixel): what the later kernels read
+  int* rs = run_label + (size_t)n * 2 * hw;           // slot by run id of the root run (this kernel's own look-ups)
+  int* rl = rs + hw;                                  // label by run id of the root run
+  CompRec* cr = comps + (size_t)n * max_comps;
+  int n_roots;
+  {
+    auto roots_of = [&](int wi) -> unsigned {                     // start bits of this word whose run is a filled root
+      unsigned st = S[wi] & X[wi], out = 0u;
+      while (st) { const int b = __ffs(st) - 1; st &= st - 1; const int r = runid(wi, b); if (par[r] == r) out |= 1u << b; }
+      return out;
+    };
+    int c = 0;
+    for (int k = 0; k < chunk; ++k) { const int wi = tid * chunk + k; if (wi < NW) c += __popc(roots_of(wi)); }
+    int slot = block_scan(c);
+    n_roots = scr[0];
+    for (int k = 0; k < chunk; ++k) {
+      const int wi = tid * chunk + k;
+      if (wi >= NW) break;
+      unsigned rb = roots_of(wi);
+      while (rb) {
+        const int b = __ffs(rb) - 1; rb &= rb - 1;
+        const int r = runid(wi, b);
+        const int label = (wi / WPR) * w + (wi % WPR) * 32 + b;
+        so[label] = slot; rs[r] = slot; rl[r] = label;
+        if (slot < max_comps) {
+          CompRec rec; rec.label = label; rec.xmin = w; rec.ymin = h; rec.xmax = -1; rec.ymax = -1;
+          rec.n_pixels = 0; rec.n_filled = 0; rec.q3 = 0; rec.q4 = 0;
+          cr[slot] = rec;
+          for (int q = 0; q < n_cls; ++q) cls_sums[((size_t)n * max_comps + slot) * n_cls + q] = 0ull;
+        }
+        ++slot;
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- H: per-run reductions.  Thread = word; every filled run that STARTS in the word is followed to its end.
+  //   2x2 windows are attributed by their bottom row: a window whose bottom-right pixel x is filled belongs to x's run
+  //   (BL = filled bit left of x, TL / TR the two bits above); a window whose bottom-right pixel is empty but whose
+  //   bottom-left pixel ends a run can only reach 3 (both pixels above filled).
+  for (int wi = tid; wi < NW; wi += CCL_IMG_THREADS) {
+    const int y = wi / WPR, wd0 = wi - y * WPR;
+    unsigned st = S[wi] & X[wi];
+    while (st) {
+      const int b0 = __ffs(st) - 1; st &= st - 1;
+      const int r = runid(wi, b0);
+      const int slot = rs[par[r]];
+      if (slot >= max_comps) continue;
+      const bool fgrun = (F[wi] >> b0) & 1u;
+      int q3 = 0, q4 = 0, len = 0, xend = 0;
+      // walk the words of the run
+      int wd = wd0, lo = b0;
+      while (true) {
+        const int cw = y * WPR + wd;
+        const unsigned above_lo = lo == 31 ? 0u : (0xFFFFFFFFu << (lo + 1));
+        const unsigned nxt = S[cw] & above_lo & (wd == wd0 ? 0xFFFFFFFFu : 0xFFFFFFFFu);
+        unsigned stops = wd == wd0 ? nxt : S[cw];                 // the run ends before the next start bit
+        const unsigned v = valid(wd);
+        int hi;
+        bool ended;
+        if (stops) { hi = __ffs(stops) - 2; ended = true; }
+        else { hi = 31 - __clz(v); ended = wd == WPR - 1; }
+        if (hi >= lo) {
+          const unsigned M = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+          const unsigned xs = (X[cw] << 1) | (wd > 0 ? (X[cw - 1] >> 31) : 0u);
+          const unsigned T = y > 0 ? X[cw - WPR] : 0u;
+          const unsigned ts = y > 0 ? ((T << 1) | (wd > 0 ? (X[cw - WPR - 1] >> 31) : 0u)) : 0u;
+          q4 += __popc(M & xs & ts & T);
+          q3 += __popc(M & ((xs & ts & ~T) | (xs & ~ts & T) | (~xs & ts & T)));
+          len += hi - lo + 1;
+          xend = wd * 32 + hi;
+        }
+        if (ended) break;
+        ++wd; lo = 0;
+      }
+      // window right of the run's last pixel (bottom-right empty, bottom-left = last pixel): 3 iff both pixels above are filled
+      if (y > 0) {
+        const int xr = xend + 1;
+        const bool br = xr < w && ((X[y * WPR + (xr >> 5)] >> (xr & 31)) & 1u);
+        if (!br) {
+          const bool tl = (X[(y - 1) * WPR + (xend >> 5)] >> (xend & 31)) & 1u;
+          const bool tr = xr < w && ((X[(y - 1) * WPR + (xr >> 5)] >> (xr & 31)) & 1u);
+          q3 += tl && tr;
+        }
+      }
+      CompRec* rec = cr + slot;
+      if (q3) atomicAdd(&rec->q3, q3);
+      if (q4) atomicAdd(&rec->q4, q4);
+      atomicAdd(&rec->n_filled, len);
+      if (fgrun) atomicAdd(&rec->n_pixels, len);
+      atomicMin(&rec->xmin, wd0 * 32 + b0); atomicMin(&rec->ymin, y);
+      atomicMax(&rec->xmax, xend); atomicMax(&rec->ymax, y);
+    }
+  }
+  // ---- I: labels to global memory (and the class vote sums), one warp per row, lane = pixel
+  int* lab = labels + (size_t)n * hw;
+  for (int y = wid; y < h; y += NWARP) {
+    for (int wd = 0; wd < WPR; ++wd) {
+      const int x = wd * 32 + lane, wi = y * WPR + wd;
+      const bool own = x < w && ((X[wi] >> lane) & 1u);
+      int slot = -1;
+      if (x < w) {
+        int l = -1;
+        if (own) { const int root = par[runid(wi, lane)]; l = rl[root]; slot = rs[root]; }
+        lab[(size_t)y * w + x] = l;
+      }
+      if (n_cls > 0) {
+        if (slot >= max_comps) slot = -1;
+        const unsigned active = __ballot_sync(0xffffffffu, slot >= 0);
+        if (slot >= 0) {
+          const unsigned grp = __match_any_sync(active, slot);
+          const int leader = __ffs(grp) - 1;
+          const float* lg = cls_logits + ((size_t)n * hw + (size_t)y * w + x) * cls_stride;
+          float e[UBD_MAX_CLASSES];
+          float mx = lg[0];
+          for (int c = 1; c < n_cls; ++c) mx = fmaxf(mx, lg[c]);
+          float s = 0.f;
+          for (int c = 0; c < n_cls; ++c) { e[c] = expf(lg[c] - mx); s += e[c]; }
+          for (int c = 0; c < n_cls; ++c) {
+            const unsigned fx = (unsigned)(e[c] / s * 16777216.0f);
+            const unsigned tot = __reduce_add_sync(grp, fx);
+            if (lane == leader && tot) atomicAdd(&cls_sums[((size_t)n * max_comps + slot) * n_cls + c], (unsigned long long)tot);
+          }
+        }
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  // ---- J: kept components of this image (2*contourArea > min_area_x2, utils.py:55)
+  {
+    const int cntc = min(n_roots, max_comps);
+    int k = 0;
+    for (int s = tid; s < cntc; s += CCL_IMG_THREADS) {
+      const volatile CompRec* r = cr + s;
+      k += (2 * r->q4 + r->q3) > min_area_x2;
+    }
+    k = __reduce_add_sync(0xffffffffu, k);
+    __syncthreads();
+    if (lane == 0) scr[1 + wid] = k;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int i = 0; i < NWARP; ++i) t += scr[1 + i];
+      n_comps[n] = n_roots;
+      kept_count[n] = t;
+      atomicAdd(&totals->total_kept, t);
+      atomicMax(&totals->max_ncomp, n_roots);
+    }
+  }
+}

@@ -51,6 +51,11 @@ struct ubd_handle_s {
   bool have_weights = false;
   bool tc_weights_dirty = true;   // tensor-core weight images must be rebuilt from d_params
   bool tc4_weights_dirty = true;  // ... the column-rotating kernel's weight images (ubd_tc4.cuh)
+  int opt_pipeline = 0;           // dilated stack: 1 = one layer-pipelined launch with L2 ring buffers for chunks of >= 24 images
+                                  // (measured 0.84 ms vs 0.83 ms per 64 x 1024^2 for one launch per layer, profiles/r02_summary.md)
+  int opt_pipe_ring = 3;          // maps per layer boundary in that launch
+  DevBuf pipe_ring, pipe_flags;
+  long long pipe_tag = 0;
   int opt_tc_variant = 1;         // dilated layers: 1 = ubd_tc4.cuh, 0 = ubd_tc.cuh (see launch_dil_tc)
 
   int opt_stem_variant = 0;       // grey input: 2 = fused separable kernel (ubd_stemf.cuh), 1 = two-kernel paths, 0 = auto (stem_is_fused)
@@ -69,7 +74,7 @@ struct ubd_handle_s {
   int map_h = 0, map_w = 0, map_n = 0, map_prec = -1;
   long long act2_tag = 0;                  // geometry the parity-split act2 buffer was last zeroed for     // shape the padded maps were last zeroed for
   DevBuf outer;
-  DevBuf parent, labels, slot_of, comps, cls_sums, out_index, row_ext;
+  DevBuf parent, labels, slot_of, comps, cls_sums, out_index, row_ext, run_label;
   DevBuf prep_tab, prep_a, prep_b, prep_in, prep_out;     // input-side resize tables and intermediates (ubd_prep.cuh)
   DevBuf l2dense;                 // merged dense 3x3 kernel of the stem's L2 (+ bias)
   DevBuf stem_wimg;               // pointwise B images of L2 / L3 for the tensor-core stem
@@ -91,8 +96,8 @@ struct ubd_handle_s {
 
   std::vector<DevBuf*> all_bufs() {
     return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &out_index, &row_ext, &rs[0].hdr, &rs[0].out_recs, &rs[0].hull_pts, &rs[0].box_recs, &rs[1].box_recs, &rs[0].d_images, &rs[0].d_mask, &rs[0].d_logits,
-            &rs[1].hdr, &rs[1].out_recs, &rs[1].hull_pts, &rs[1].d_images, &rs[1].d_mask, &rs[1].d_logits, &prep_tab, &prep_a, &prep_b, &prep_in, &prep_out, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
+            &cls_sums, &out_index, &row_ext, &run_label, &rs[0].hdr, &rs[0].out_recs, &rs[0].hull_pts, &rs[0].box_recs, &rs[1].box_recs, &rs[0].d_images, &rs[0].d_mask, &rs[0].d_logits,
+            &rs[1].hdr, &rs[1].out_recs, &rs[1].hull_pts, &rs[1].d_images, &rs[1].d_mask, &rs[1].d_logits, &pipe_ring, &pipe_flags, &prep_tab, &prep_a, &prep_b, &prep_in, &prep_out, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
   }
 };

@@ -124,6 +124,26 @@ template <bool BF16> struct Smem {
   __align__(16) float l1w[12 + UBD_NF + UBD_NF]; // dw1[9] (+3 pad), pw1[24], b1[24] (grey input)
 };
 
+// Layer-pipelined launch (PIPE): the six dilated layers run CONCURRENTLY on disjoint groups of CTAs (CTA b works on layer
+// b % 6; its group splits every image's rows among its members), chained image by image through ring buffers of
+// `ring_imgs` maps per layer boundary that are meant to stay in L2, and every CTA keeps ONE layer's weight images for the
+// whole launch.  done[layer * n_imgs + image] counts the epilogue warps of that layer's CTAs that have finished the image
+// (release: __threadfence + atomicAdd; acquire: ld.acquire.gpu by the producer warp, then a proxy fence before the
+// bulk copies read the map).  A layer starts image m when the layer before it has finished m and the layer after it
+// has finished m - ring_imgs (its ring slot is free).
+struct PipeArgs { uint4* ring; int* done; int ring_imgs; long long img_units; };
+
+__device__ __forceinline__ bool pipe_wait(const int* flag, int target, volatile int* abort_flag, int* gerr, int code) {
+  uint32_t polls = 0;
+  while (true) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= target) return true;
+    if (*abort_flag || ++polls > 8000000u) { atomicCAS(gerr, 0, code); *abort_flag = 1; return false; }
+    __nanosleep(32);
+  }
+}
+
 // A contiguous run of output rows inside one (image, strip, y-phase).
 struct Piece { int n, x0, nw, c, j0, rows, R; };
 
@@ -174,12 +194,30 @@ __device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t adesc,
 // logit threshold (net.py:307-311, model_runner.py:124): the last map never reaches HBM.
 // out_mode 3: parity-split output [n][y][x & 1][plane][PAD + (x >> 1)] (input of the stride-2 layer).
 // L1SRC: `in` is the uint8 grey image, h / w the half-resolution map size, d = 1 (see tc::L1Args).
-template <bool BF16, bool L1SRC>
+template <bool BF16, bool L1SRC, bool PIPE = false>
 __global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
-dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ wb,
-                   int n_imgs, int h, int w, int d, int sw, int out_mode, int out_pad, int* gerr, HeadArgs head, long long* trace,
-                   tc::L1Args l1) {
+dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, const uint8_t* __restrict__ wb_,
+                   int n_imgs, int h, int w, int d_, int sw, int out_mode_, int out_pad, int* gerr, HeadArgs head, long long* trace,
+                   tc::L1Args l1, PipeArgs pipe) {
   using S_t = Smem<BF16>;
+  // PIPE: this CTA's layer, its index inside the layer's group and the group size; else one layer for the whole grid
+  int layer = 0, kidx = (int)blockIdx.x, K = (int)gridDim.x;
+  const uint4* in = in_;
+  uint4* out = out_;
+  const uint8_t* wb = wb_;
+  int d = d_, out_mode = out_mode_;
+  if constexpr (PIPE) {
+    layer = (int)blockIdx.x % UBD_NLAYERS_DIL;
+    kidx = (int)blockIdx.x / UBD_NLAYERS_DIL;
+    K = ((int)gridDim.x - layer + UBD_NLAYERS_DIL - 1) / UBD_NLAYERS_DIL;
+    d = layer == 1 ? 2 : (layer == 2 ? 4 : (layer == 3 ? 8 : (layer == 4 ? 16 : 1)));
+    wb = wb_ + (size_t)layer * S_t::WB;
+    out_mode = layer == UBD_NLAYERS_DIL - 1 ? 2 : 0;
+    if (layer > 0) in = pipe.ring + (size_t)(layer - 1) * pipe.ring_imgs * pipe.img_units;
+    out = pipe.ring + (size_t)layer * pipe.ring_imgs * pipe.img_units;
+  }
+  const int n_outer = PIPE ? n_imgs : 1;                     // PIPE: the roles walk image by image
+  auto make_walk = [&](int m) { return PIPE ? Walk(1, h, w, d, sw, (kidx + m) % K, K) : Walk(n_imgs, h, w, d, sw, kidx, K); };
   constexpr int NS = S_t::NS;
   constexpr int NGI = BF16 ? 3 : UBD_NG;
   constexpr uint32_t WBB = S_t::WB;
@@ -252,7 +290,6 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
   const uint32_t plane_bytes = (uint32_t)(sw + 2 * PAD) * 16;
   const uint32_t slot_bytes = (uint32_t)NGI * plane_bytes;
   const bool one_copy = (w == sw);
-  Walk walk(n_imgs, h, w, d, sw, (int)blockIdx.x, (int)gridDim.x);
   Piece pc;
   uint64_t* gfull = S.gfull + seg * 4;
   uint64_t* gempty = S.gempty + seg * 4;
@@ -265,7 +302,23 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     }
     uint32_t lseq = 0;
     bool ok = !L1SRC;                                      // L1SRC: the rows come from the L1 warps below
+    for (int m = 0; m < n_outer && ok; ++m) {
+    Walk walk = make_walk(m);
+    if constexpr (PIPE) {
+      // the layer before has finished this image, and the layer after has finished the image whose ring slot we reuse
+      bool okf = true;
+      if (lane == 0) {
+        const int g = (int)gridDim.x;
+        if (layer > 0) okf = pipe_wait(pipe.done + (size_t)(layer - 1) * n_imgs + m, 8 * ((g - (layer - 1) + UBD_NLAYERS_DIL - 1) / UBD_NLAYERS_DIL), abort_flag, gerr, 27);
+        if (okf && layer < UBD_NLAYERS_DIL - 1 && m >= pipe.ring_imgs)
+          okf = pipe_wait(pipe.done + (size_t)(layer + 1) * n_imgs + m - pipe.ring_imgs, 8 * ((g - (layer + 1) + UBD_NLAYERS_DIL - 1) / UBD_NLAYERS_DIL), abort_flag, gerr, 28);
+        asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this SM's bulk copies
+      }
+      ok = __all_sync(0xffffffffu, okf);
+    }
     while (ok && walk.next(pc)) {
+      if constexpr (PIPE) pc.n = m;
+      const int in_n = PIPE ? (layer == 0 ? pc.n : pc.n % pipe.ring_imgs) : pc.n;
       const uint32_t copy_bytes = (uint32_t)(pc.nw + 2 * PAD) * 16;
       for (int i = 0; i < pc.rows + 2 && ok; ++i) {
         const int jj = pc.j0 - 1 + i;
@@ -278,7 +331,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         const uint32_t bar = smem_u32(&S.full[slot]);
         const uint32_t dst = slots0 + slot * S_t::SLOT;
         const int y = pc.c + jj * d;
-        const uint4* src = in + (((size_t)pc.n * h + y) * NGI) * wp + pc.x0;
+        const uint4* src = in + (((size_t)in_n * h + y) * NGI) * wp + pc.x0;
         if (elect_one()) {
           if (one_copy) {
             // the strip spans the image: its x padding is zero (cleared once above), copy the interior only
@@ -295,6 +348,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         ++lseq;
       }
     }
+    }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------------------------ MMA issuers (segment 0 / 1)
     bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 22);
@@ -307,6 +361,8 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
                                  : ((1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24));
     const uint32_t tmem_t = tmem_base + (uint32_t)seg * 128u;
     uint32_t lseq = 0, par_e = 0;
+    for (int m = 0; m < n_outer && ok; ++m) {
+    Walk walk = make_walk(m);
     while (ok && walk.next(pc)) {
       const bool active = seg * SEG < pc.nw;                 // a narrow strip has no second segment
       for (int i = 0; i < pc.rows + 2 && ok; ++i) {
@@ -383,12 +439,17 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         if (warp == 1) { TC4_TRACE(1, 3); TC4_TRACE_NEXT(); }
       }
     }
+    }
   } else if (epi) {
     // ------------------------------------------------------------------ epilogue (lane = pixel, 24 columns = channels)
     const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)seg * 128u;
     bool ok = true;
     uint32_t par_f = 0;
+    for (int m = 0; m < n_outer && ok; ++m) {
+    Walk walk = make_walk(m);
     while (ok && walk.next(pc)) {
+      if constexpr (PIPE) pc.n = m;
+      const int out_n = PIPE ? pc.n % pipe.ring_imgs : pc.n;   // ring slot of the output map (the head writes by image index)
       if (seg * SEG >= pc.nw) continue;
       for (int o = 0; o < pc.rows && ok; ++o) {
         const uint32_t G = (uint32_t)(o & 3);
@@ -448,13 +509,13 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
             }
           } else if (BF16 && out_mode == 0) {
             // (streaming stores: the next layer reads this map after the whole sweep, long after L2 has turned over)
-            uint4* o_px = out + (((size_t)pc.n * h + y) * 3) * wpo + out_pad + x;
+            uint4* o_px = out + (((size_t)out_n * h + y) * 3) * wpo + out_pad + x;
 #pragma unroll
             for (int g = 0; g < 3; ++g)
               __stcs(o_px + (size_t)g * wpo, make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
                                                         pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7])));
           } else {
-            uint4* o_px = out + (((size_t)pc.n * h + y) * UBD_NG) * wpo + out_pad + x;
+            uint4* o_px = out + (((size_t)out_n * h + y) * UBD_NG) * wpo + out_pad + x;
             const bool rnd = !BF16 && out_mode == 0;
 #pragma unroll
             for (int g = 0; g < UBD_NG; ++g) {
@@ -466,6 +527,13 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
         }
         if (warp == 4) { TC4_TRACE(2, 3); TC4_TRACE_NEXT(); }
       }
+    }
+    if constexpr (PIPE) {
+      // this warp's part of image m is stored: publish it (release) to the next layer's producers and the previous layer's
+      __threadfence();
+      __syncwarp();
+      if (ok && lane == 0) atomicAdd(pipe.done + (size_t)layer * n_imgs + m, 1);
+    }
     }
   }
 
@@ -488,6 +556,7 @@ dilconv_col_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const 
     for (int i = 0; i < 9; ++i) dwr[i] = S.l1w[i];
     uint32_t lseq = 0, ring_slot = 0, ring_phase = 0;        // ring position = (lseq % NS, (lseq / NS) & 1)
     bool ok = true;
+    Walk walk = make_walk(0);
     while (ok && walk.next(pc)) {
       const int x = pc.x0 - 1 + t;                           // this thread's map column
       const bool use = lane < L1_PXW && t < pc.nw + 2;
@@ -668,6 +737,8 @@ static void tc4_setup_attributes() {
   cudaFuncSetAttribute(tc4::dilconv_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
   cudaFuncSetAttribute(tc4::dilconv_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<false>));
   cudaFuncSetAttribute(tc4::dilconv_col_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<false>));
+  cudaFuncSetAttribute(tc4::dilconv_col_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc4::Smem<true>));
 }
 
 // Weight images, rebuilt whenever the parameters change (tc_prepare owns the error flag and the offsets table).
@@ -716,10 +787,61 @@ static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer
   if (l1) la = *l1;
 #define UBD_TC4_LAUNCH(BF, L1S, THR)                                                                                   \
   tc4::dilconv_col_kernel<BF, L1S><<<grid, THR, sizeof(tc4::Smem<BF>), h->stream>>>(                                   \
-      (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p, la)
+      (const uint4*)in, (uint4*)out, wb, n, hh, ww, d, sw, out_mode, out_pad, tc_err_flag(h), ha, (long long*)h->tc_trace.p, la, tc4::PipeArgs{})
   if (l1) { if (bf16) UBD_TC4_LAUNCH(true, true, tc4::THREADS_L1); else UBD_TC4_LAUNCH(false, true, tc4::THREADS_L1); }
   else { if (bf16) UBD_TC4_LAUNCH(true, false, tc4::THREADS); else UBD_TC4_LAUNCH(false, false, tc4::THREADS); }
 #undef UBD_TC4_LAUNCH
+  ++h->launches;
+  UBD_CUDA(cudaGetLastError());
+  return UBD_OK;
+}
+
+// All six dilated layers + head of `n` images in ONE launch, layer-pipelined over CTA groups with ring buffers between the
+// layers (see tc4::PipeArgs).  in: the stem's output maps of the n images; the head writes head->logits / mask.
+// Measured on B200, 64 x 1024^2 tf32 (profiles/r02_summary.md): 0.84 ms (ring 3) against 0.83 ms for one launch per layer,
+// DRAM traffic 2.6 GB against 4.2 GB: a group of 25 CTAs splits an image into 10-row pieces, whose two halo rows each cost
+// a fifth of the staging and tensor work, and 106 MB of rings do not stay resident in the 126 MB L2 (hit rate 41 %).
+static int tc4_launch_pipeline(ubd_handle h, const void* in, int n, int hh, int ww, const tc::HeadArgs* head) {
+  if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
+  int rc = tc4_prepare(h);
+  if (rc) return rc;
+  const bool bf16 = h->precision == UBD_BF16;
+  const int ring = std::max(2, h->opt_pipe_ring);
+  const size_t img_units = act_elems(1, hh, ww, UBD_MAP_PAD) / (bf16 ? 2 : 1);               // 16-byte units per map
+  const size_t ring_bytes = (size_t)(UBD_NLAYERS_DIL - 1) * ring * img_units * 16;
+  const long long tag = ((long long)h->precision << 56) ^ ((long long)ring << 48) ^ ((long long)hh << 24) ^ (long long)ww;
+  if (h->pipe_ring.cap < ring_bytes) {
+    if (h->pipe_ring.p) cudaFree(h->pipe_ring.p);
+    h->pipe_ring.p = nullptr; h->pipe_ring.cap = 0;
+    UBD_CUDA(cudaMalloc(&h->pipe_ring.p, ring_bytes));
+    h->pipe_ring.cap = ring_bytes;
+    h->pipe_tag = 0;
+  }
+  if (h->pipe_tag != tag) {                 // the x padding of the ring maps is the convolutions' zero padding
+    UBD_CUDA(cudaMemsetAsync(h->pipe_ring.p, 0, h->pipe_ring.cap, h->stream));
+    h->pipe_tag = tag;
+  }
+  const size_t flag_bytes = (size_t)UBD_NLAYERS_DIL * n * sizeof(int);
+  if (h->pipe_flags.cap < flag_bytes) {
+    if (h->pipe_flags.p) cudaFree(h->pipe_flags.p);
+    h->pipe_flags.p = nullptr; h->pipe_flags.cap = 0;
+    UBD_CUDA(cudaMalloc(&h->pipe_flags.p, flag_bytes + 1024));
+    h->pipe_flags.cap = flag_bytes + 1024;
+  }
+  UBD_CUDA(cudaMemsetAsync(h->pipe_flags.p, 0, flag_bytes, h->stream));
+  const uint8_t* base = (const uint8_t*)h->tc4_weights.p;
+  const uint8_t* wb = bf16 ? base + kTc4Tf32 : base;
+  const int sw = ww <= tc4::SW_MAX ? ww : tc4::SW_MAX;
+  const int grid = h->n_sm;
+  tc::HeadArgs ha{};
+  if (head) ha = *head;
+  tc4::PipeArgs pa{(uint4*)h->pipe_ring.p, (int*)h->pipe_flags.p, ring, (long long)img_units};
+  if (bf16)
+    tc4::dilconv_col_kernel<true, false, true><<<grid, tc4::THREADS, sizeof(tc4::Smem<true>), h->stream>>>(
+        (const uint4*)in, nullptr, wb, n, hh, ww, 1, sw, 0, UBD_MAP_PAD, tc_err_flag(h), ha, (long long*)h->tc_trace.p, tc::L1Args{}, pa);
+  else
+    tc4::dilconv_col_kernel<false, false, true><<<grid, tc4::THREADS, sizeof(tc4::Smem<false>), h->stream>>>(
+        (const uint4*)in, nullptr, wb, n, hh, ww, 1, sw, 0, UBD_MAP_PAD, tc_err_flag(h), ha, (long long*)h->tc_trace.p, tc::L1Args{}, pa);
   ++h->launches;
   UBD_CUDA(cudaGetLastError());
   return UBD_OK;
