@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="BASELINE.json configs[1] (default), [2] or [3]")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--size", type=int, default=0, help="square image side (default: the config's shape)")
-    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", ""), choices=["", "fp32", "tf32", "bf16"],
+    ap.add_argument("--precision", default=os.environ.get("UBD_PRECISION", ""), choices=["", "fp32", "tf32", "bf16", "f16"],
                     help="default: the config's (configs[1] is quoted as fp32/TF32: tf32 tensor-core path)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -285,7 +285,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     eng = Engine(device=local_rank, precision=precision, n_classes=n_classes)
     eng.set_weights(weights)
-    for opt in ("tc_variant", "dense_l2", "stem_chunk", "stem_variant", "chunk", "fused_ccl", "gpu_boxes", "pipeline", "pipe_ring"):
+    for opt in ("tc_variant", "dense_l2", "stem_chunk", "stem_variant", "chunk", "fused_ccl", "gpu_boxes", "pipeline", "pipe_ring", "cc_stream"):
         if os.environ.get("UBD_" + opt.upper()):
             eng.set_option(opt, int(os.environ["UBD_" + opt.upper()]))
     # two different batches alternate, so that nothing of step k is still in L2 for step k+1
@@ -295,6 +295,7 @@ def main():
     d_imgs = [p.cuda(non_blocking=False) for p in pinned]
     min_area_x2 = 10
     cap = 256 * B
+    DEPTH = max(1, min(3, int(os.environ.get("UBD_DEPTH", "3"))))      # batches in flight through submit / wait
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
@@ -306,14 +307,14 @@ def main():
                 _, counts = eng.segment_dev(d_imgs[k & 1].data_ptr(), _lib.UBD_U8, B, H, W, thr, min_area_x2, _lib.PREPROC_MOBILENET,
                                             max_comps=cap)
             return counts
-        pend = None
+        pend = []
         for k in range(steps):
-            t = eng.segment_submit(None, thr, min_area_x2, _lib.PREPROC_MOBILENET, max_comps=cap,
-                                   device_ptr=d_imgs[k & 1].data_ptr(), shape=(B, H, W), dtype=_lib.UBD_U8)
-            if pend is not None:
-                _, counts = eng.segment_wait(pend)
-            pend = t
-        _, counts = eng.segment_wait(pend)
+            pend.append(eng.segment_submit(None, thr, min_area_x2, _lib.PREPROC_MOBILENET, max_comps=cap,
+                                           device_ptr=d_imgs[k & 1].data_ptr(), shape=(B, H, W), dtype=_lib.UBD_U8))
+            if len(pend) == DEPTH:
+                _, counts = eng.segment_wait(pend.pop(0))
+        while pend:
+            _, counts = eng.segment_wait(pend.pop(0))
         return counts
 
     def barrier():
@@ -344,7 +345,7 @@ def main():
 
     # end to end through the host-buffer C-ABI calls (what ModelRunner.predict / predict_stream do): pinned host
     # images in, mask + components out, every copy inside the timed region
-    mask_h = [torch.empty((B, H // 4, W // 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+    mask_h = [torch.empty((B, H // 4, W // 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(DEPTH)]
 
     def run_e2e(steps):
         counts_h = None
@@ -356,13 +357,13 @@ def main():
                                                              np.float32(thr), min_area_x2, _lib.ptr(mask_h[k & 1]), None, None,
                                                              _lib.ptr(comps_h), cap, _lib.ptr(counts_h)))
             return counts_h
-        pend = None
+        pend = []
         for k in range(steps):
-            t = eng.segment_submit(h_imgs[k & 1], thr, min_area_x2, _lib.PREPROC_MOBILENET, mask_out=mask_h[k & 1], max_comps=cap)
-            if pend is not None:
-                _, counts_h = eng.segment_wait(pend)
-            pend = t
-        _, counts_h = eng.segment_wait(pend)
+            pend.append(eng.segment_submit(h_imgs[k & 1], thr, min_area_x2, _lib.PREPROC_MOBILENET, mask_out=mask_h[k % DEPTH], max_comps=cap))
+            if len(pend) == DEPTH:
+                _, counts_h = eng.segment_wait(pend.pop(0))
+        while pend:
+            _, counts_h = eng.segment_wait(pend.pop(0))
         return counts_h
 
     run_e2e(max(2, args.warmup // 2))
@@ -459,9 +460,9 @@ def main():
                 "host_ms_per_step": dict(zip(["enqueue_forward", "enqueue_cc", "wait_counts", "read_records", "boxes"], host_ms))}
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[precision],
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "f16": "f16"}[precision],
                 "data": "synthetic", "config": cfg, "clocks": clk.summary(),
-                "api": "ubd_segment_dev / ubd_segment" if args.sync_api else "ubd_segment_submit[_dev] + ubd_segment_wait (two batches in flight)",
+                "api": "ubd_segment_dev / ubd_segment" if args.sync_api else f"ubd_segment_submit[_dev] + ubd_segment_wait ({DEPTH} batches in flight)",
                 "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(imgs[0].nbytes),
                         "d2h_bytes_per_step": int(mask_h[0].nbytes + 4 * B + 44 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum()),

@@ -46,7 +46,10 @@ typedef enum { UBD_PREPROC_NONE = 0,                               /* net.py:164
                UBD_PREPROC_MOBILENET = 1 } ubd_preproc;            /* net.py:217-218     */
 typedef enum { UBD_FP32 = 0,      /* FP32 CUDA-core path (exact mode)                    */
                UBD_TF32 = 1,      /* tcgen05 kind::tf32 implicit GEMM for the dilated layers */
-               UBD_BF16 = 2 } ubd_precision;
+               UBD_BF16 = 2,      /* bf16 maps and weights, fp32 accumulate                                  */
+               UBD_F16 = 3 }      /* IEEE-half maps and weights (the 10-bit significand of tf32 in 16 bits), fp32
+                                     accumulate: tf32's accuracy at bf16's traffic; activations must stay below 65504 */
+               ubd_precision;
 
 #define UBD_N_WEIGHT_ARRAYS 23    /* model.get_weights() of net.py:286-313    */
 #define UBD_MAX_CLASSES 32
@@ -128,9 +131,9 @@ int ubd_forward_dev(ubd_handle h, const void* d_images, int in_dtype, int n, int
  * batch): submit queues one batch - host-to-device copy of the images, network, threshold, CC kernels, the
  * copies of mask / logits back to mask_out / logits_out (nullable; must stay valid until the wait) - and returns a
  * ticket; wait blocks until that batch is finished, computes its boxes on the host and fills comps_out
- * (capacity max_comps >= the value given to submit) and n_comps_per_image.  At most two batches may be in flight
- * and tickets are collected in submission order: the copy of batch k+1 and the host part of batch k then run under
- * the kernels of the other batch.  Pass pinned host memory for the copies to be asynchronous.  The _dev form
+ * (capacity max_comps >= the value given to submit) and n_comps_per_image.  At most three batches may be in flight
+ * and tickets are collected in submission order: the copies of batches k+1, k+2 and the host part of batch k then run
+ * under the kernels of the others, and the CC stage of batch k overlaps the network of batch k+1.  Pass pinned host memory for the copies to be asynchronous.  The _dev form
  * takes images already resident on the handle's device.  The synchronous entry points return UBD_ERR_STATE while
  * a submitted batch is in flight. */
 int ubd_segment_submit(ubd_handle h, const void* images, int in_dtype, int n, int height, int width,

@@ -159,7 +159,7 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("precision", ["tf32", "fp32"])
 def test_pipelined_submit_wait_equals_predict(precision):
-    """ubd_segment_submit / ubd_segment_wait (two batches in flight, ModelRunner.predict_stream) return exactly what
+    """ubd_segment_submit / ubd_segment_wait (three batches in flight, ModelRunner.predict_stream) return exactly what
     the synchronous ModelRunner.predict returns, batch by batch, for batches of different sizes and shapes."""
     from ubdvss_b200 import _lib
     from ubdvss_b200.model_runner import ModelRunner
@@ -178,14 +178,16 @@ def test_pipelined_submit_wait_equals_predict(precision):
         assert np.array_equal(d0, d1) and np.array_equal(c0, c1)
         assert [[(tuple(o.bbox), getattr(o, "object_type", None)) for o in f] for f in f0] == \
                [[(tuple(o.bbox), getattr(o, "object_type", None)) for o in f] for f in f1]
-    # call-order errors: a third submit, a synchronous call while batches are in flight, collecting out of order
+    # call-order errors: a fourth submit, a synchronous call while batches are in flight, collecting out of order
     t0 = model.segment_submit(batches[0], np.float32(0.0), 10, preprocessing="mobilenet_like")
     t1 = model.segment_submit(batches[1], np.float32(0.0), 10, preprocessing="mobilenet_like")
+    t2 = model.segment_submit(batches[4], np.float32(0.0), 10, preprocessing="mobilenet_like")
     for bad in (lambda: model.segment_submit(batches[2], np.float32(0.0), 10), lambda: runner.predict(model, batches[0]),
-                lambda: model.segment_wait(t1)):
+                lambda: model.segment_wait(t1), lambda: model.segment_wait(t2)):
         with pytest.raises(_lib.UbdError) as err:
             bad()
         assert err.value.code in (-6,)
     model.segment_wait(t0)
     model.segment_wait(t1)
+    model.segment_wait(t2)
     assert model.predict(batches[3]).shape == (4, 16, 16, 1 + n_classes)

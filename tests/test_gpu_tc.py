@@ -75,6 +75,28 @@ def test_bf16_layer_matches_oracle(eng, layer, shape):
     assert np.abs(got - ref).max() <= 2e-4, np.abs(got - ref).max()
 
 
+@pytest.mark.parametrize("layer", range(6))
+@pytest.mark.parametrize("shape", [(2, 64, 128), (3, 20, 36), (1, 136, 240), (3, 160, 528)])
+def test_f16_layer_matches_oracle(eng, layer, shape):
+    """kind::f16 with IEEE-half operands (precision "f16": the significand of tf32 in a 16-bit container), fp32 accumulate:
+    against the oracle on half-rounded inputs and weights only the accumulation order remains.  Interleaved with bf16
+    calls on the same handle: the 16-bit weight images are rebuilt when the container changes."""
+    rng = np.random.default_rng(layer * 10 + shape[1])
+    x = np.maximum(rng.normal(0, 1, size=shape + (24,)), 0).astype(np.float16).astype(np.float32)
+    w = onet.init_weights(0, seed=1234)
+    got = eng.debug_dilated_layer(x, layer, "f16")
+    k, b = w[9 + 2 * layer].astype(np.float16).astype(np.float32), w[10 + 2 * layer]
+    ref = np.maximum(onet._conv3x3_np(x.astype(np.float64), k.astype(np.float64), onet.DILATIONS[layer]) + b, 0)
+    assert np.abs(got - ref).max() <= 2e-4, np.abs(got - ref).max()
+    if layer == 2:
+        xb = _round_bf16(x)
+        gb = eng.debug_dilated_layer(xb, layer, "bf16")
+        kb = _round_bf16(w[9 + 2 * layer])
+        refb = np.maximum(onet._conv3x3_np(xb.astype(np.float64), kb.astype(np.float64), onet.DILATIONS[layer]) + b, 0)
+        assert np.abs(gb - refb).max() <= 2e-4
+        assert np.array_equal(eng.debug_dilated_layer(x, layer, "f16"), got)
+
+
 def test_tf32_operands_are_truncated(eng):
     """kind::tf32 ignores the low 13 mantissa bits of its operands: garbage there must not change the
     result.  (The stem's L1 producers rely on it: they round by adding half a tf32 ulp without masking.)"""

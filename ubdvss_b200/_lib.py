@@ -12,8 +12,8 @@ LIB_PATH = os.path.join(HERE, "csrc", "libubd.so")
 
 UBD_U8, UBD_F32 = 0, 1
 PREPROC_NONE, PREPROC_MOBILENET = 0, 1
-FP32, TF32, BF16 = 0, 1, 2
-PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16}
+FP32, TF32, BF16, F16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16, "f16": F16}
 N_WEIGHT_ARRAYS = 23
 
 STATUS = {0: "UBD_OK", -1: "UBD_ERR_ARG", -2: "UBD_ERR_CUDA", -3: "UBD_ERR_NO_WEIGHTS",

@@ -5,18 +5,19 @@
 
 struct DevBuf { void* p = nullptr; size_t cap = 0; };
 
-// Host-visible results of one batch (see ccl_enqueue / ccl_finish in ubd_api.cu): two slots so that a submitted batch
-// can be finished on the host while the next one runs.
+// Host-visible results of one batch (see ccl_enqueue / ccl_finish in ubd_api.cu): kSlots slots so that a submitted batch
+// can be finished on the host while the next ones run and are being copied in.
+constexpr int kSlots = 3;
 struct ResultSlot {
   DevBuf hdr, out_recs, hull_pts, box_recs;          // device: raw / kept counts + totals, kept records, hull candidates | rectangles
   bool gpu_boxes = true;
   DevBuf d_images, d_mask, d_logits;       // device: staging of a submitted batch and its outputs
   int* h_hdr = nullptr; size_t h_hdr_cap = 0;     // pinned copy of hdr (kept counts + totals)
-  cudaEvent_t ev_cc = nullptr, ev_fwd = nullptr;
+  cudaEvent_t ev_cc = nullptr, ev_fwd = nullptr, ev_in = nullptr, ev_d2h = nullptr;
   int n = 0, mh = 0, mw = 0, max_pts = 0, max_comps_img = 0, max_out = 0;
   const uint8_t* d_mask_used = nullptr; const float* d_cls_used = nullptr;
   int cls_stride = 0, n_cls = 0, min_area_x2 = 0;
-  bool busy = false;
+  bool busy = false, d2h_pending = false;
   long long ticket = 0;
   std::vector<OutRec> recs; std::vector<HullPt> pts; std::vector<BoxRec> boxes;      // host scratch, reused
   std::vector<int> row0, ext; std::vector<int32_t> xy;
@@ -33,7 +34,10 @@ struct ubd_handle_s {
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;      // H2D of chunk k+1 overlaps the compute of chunk k
   cudaStream_t d2h_stream = nullptr;       // read-back of results while the next batch computes
-  ResultSlot rs[2];
+  cudaStream_t cc_stream = nullptr;        // connected components of batch k under the network of batch k+1
+  bool opt_cc_stream = true;
+  cudaStream_t rec_stream = nullptr;       // read-back of a finished batch's records (idle except inside ubd_segment_wait)
+  ResultSlot rs[kSlots];
   long long next_ticket = 0;
   std::vector<cudaEvent_t> copy_events;
   // optional CUDA-event profiling of kernel groups (option "profile")
@@ -51,6 +55,7 @@ struct ubd_handle_s {
   bool have_weights = false;
   bool tc_weights_dirty = true;   // tensor-core weight images must be rebuilt from d_params
   bool tc4_weights_dirty = true;  // ... the column-rotating kernel's weight images (ubd_tc4.cuh)
+  int tc_w16 = -1, tc4_w16 = -1, stem_w16 = -1;   // which 16-bit container (UBD_BF16 / UBD_F16) the built images hold
   int opt_pipeline = 0;           // dilated stack: 1 = one layer-pipelined launch with L2 ring buffers for chunks of >= 24 images
                                   // (measured 0.84 ms vs 0.83 ms per 64 x 1024^2 for one launch per layer, profiles/r02_summary.md)
   int opt_pipe_ring = 3;          // maps per layer boundary in that launch
@@ -95,12 +100,18 @@ struct ubd_handle_s {
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
 
   std::vector<DevBuf*> all_bufs() {
-    return {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
-            &cls_sums, &out_index, &row_ext, &run_label, &rs[0].hdr, &rs[0].out_recs, &rs[0].hull_pts, &rs[0].box_recs, &rs[1].box_recs, &rs[0].d_images, &rs[0].d_mask, &rs[0].d_logits,
-            &rs[1].hdr, &rs[1].out_recs, &rs[1].hull_pts, &rs[1].d_images, &rs[1].d_mask, &rs[1].d_logits, &pipe_ring, &pipe_flags, &prep_tab, &prep_a, &prep_b, &prep_in, &prep_out, &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
+    std::vector<DevBuf*> v = {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
+            &cls_sums, &out_index, &row_ext, &run_label, &pipe_ring, &pipe_flags, &prep_tab, &prep_a, &prep_b, &prep_in, &prep_out,
+            &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
+    for (ResultSlot& R : rs)
+      for (DevBuf* b : {&R.hdr, &R.out_recs, &R.hull_pts, &R.box_recs, &R.d_images, &R.d_mask, &R.d_logits}) v.push_back(b);
+    return v;
   }
 };
+
+// 16-bit map containers: bf16 or IEEE half (same layouts and kernels, see tc::pack16)
+static inline bool ubd_is16(ubd_handle h) { return h->precision == UBD_BF16 || h->precision == UBD_F16; }
 
 // TF 'same' stride-2 padding before the image for even sizes is 0; FML pads 1 (net.py:229-232).
 static inline int stride2_pad(ubd_handle h) { return h->fml ? 1 : 0; }

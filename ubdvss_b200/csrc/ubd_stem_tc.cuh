@@ -30,7 +30,7 @@ constexpr int PW_IMG_BYTES = 3 * tc::B_TILE_BYTES;      // 3 K-pairs x 1 KB
 constexpr int PW_WB_BYTES = PW_IMG_BYTES + 128;         // + bias[32]
 
 // pointwise weights (1,1,24,24) [c][o] -> UMMA B image, tf32-rounded; then bias
-__global__ void build_pw_img_kernel(const float* __restrict__ params, int64_t pw_off, int64_t b_off, uint8_t* __restrict__ dst_) {
+__global__ void build_pw_img_kernel(const float* __restrict__ params, int64_t pw_off, int64_t b_off, uint8_t* __restrict__ dst_, int f16) {
   float* dst = reinterpret_cast<float*>(dst_);
   for (int i = threadIdx.x; i < PW_IMG_BYTES / 4; i += blockDim.x) {
     const int kp = i / 256, rem = i % 256;
@@ -38,7 +38,8 @@ __global__ void build_pw_img_kernel(const float* __restrict__ params, int64_t pw
     const int ic = kp * 8 + kcore * 4 + col, oc = ngroup * 8 + row;
     dst[i] = oc < UBD_NF ? tc::round_tf32(params[pw_off + ic * UBD_NF + oc]) : 0.f;
   }
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[PW_IMG_BYTES / 4 + i] = i < UBD_NF ? params[b_off + i] : 0.f;
+  for (int i = threadIdx.x; i < 32; i += blockDim.x)
+    dst[PW_IMG_BYTES / 4 + i] = i < UBD_NF ? params[b_off + i] : (i == tc::F16_FLAG_SLOT && f16 ? 1.f : 0.f);     // + 16-bit container flag
 }
 
 template <int ROWS>
@@ -87,6 +88,8 @@ __device__ __forceinline__ void pw_epilogue(PwSmem<ROWS>& S, uint32_t tmem_base,
                  : "r"(taddr + 16));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     const int y = y0 + r, x = x0 + quad * 32 + lane;
+    const bool f16 = MODE == 2 && S.bias[tc::F16_FLAG_SLOT] != 0.f;
+    (void)f16;
     if (y < Ho && x < Wo) {
       float o[UBD_NF];
 #pragma unroll
@@ -96,8 +99,8 @@ __device__ __forceinline__ void pw_epilogue(PwSmem<ROWS>& S, uint32_t tmem_base,
 #pragma unroll
         for (int g = 0; g < tc::NG_BF16; ++g)
           dst[(size_t)g * (Wo + 2 * opad)] =
-              make_uint4(tc::pack_bf16x2(o[8 * g], o[8 * g + 1]), tc::pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                         tc::pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), tc::pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+              make_uint4(tc::pack16(o[8 * g], o[8 * g + 1], f16), tc::pack16(o[8 * g + 2], o[8 * g + 3], f16),
+                         tc::pack16(o[8 * g + 4], o[8 * g + 5], f16), tc::pack16(o[8 * g + 6], o[8 * g + 7], f16));
       } else {
 #pragma unroll
         for (int g = 0; g < UBD_NG; ++g) {
@@ -504,14 +507,16 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
     h->stem_wimg.cap = 2 * stem::PW_WB_BYTES + 64;
     h->stem_weights_dirty = true;
   }
+  if (ubd_is16(h) && h->stem_w16 != h->precision) h->stem_weights_dirty = true;
   if (h->stem_weights_dirty) {
     for (int l = 1; l <= 2; ++l) {
       stem::build_pw_img_kernel<<<1, 256, 0, h->stream>>>(h->d_params, h->spec.off[3 * l + 1], h->spec.off[3 * l + 2],
-                                                          (uint8_t*)h->stem_wimg.p + (l - 1) * stem::PW_WB_BYTES);
+                                                          (uint8_t*)h->stem_wimg.p + (l - 1) * stem::PW_WB_BYTES, h->precision == UBD_F16);
       ++h->launches;
     }
     UBD_CUDA(cudaGetLastError());
     h->stem_weights_dirty = false;
+    h->stem_w16 = ubd_is16(h) ? h->precision : h->stem_w16;
   }
   if (stem_is_fused(h, in_dtype)) return stemf_launch(h, d_img, in_dtype, preproc, n, H, W, act3);
   const int p2 = stride2_pad(h);
@@ -547,7 +552,7 @@ static int run_stem_tc(ubd_handle h, const void* d_img, int in_dtype, int prepro
     const int ntiles = n * ((H2 / 2 + stem::R3 - 1) / stem::R3) * ((W2 / 2 + stem::SEGPX - 1) / stem::SEGPX);
     const int grid = std::min(ntiles, 3 * h->n_sm);
     const uint8_t* wb3 = (const uint8_t*)h->stem_wimg.p + stem::PW_WB_BYTES;
-    if (h->precision == UBD_BF16)
+    if (ubd_is16(h))
       stem::stem3_tc_kernel<2><<<grid, stem::THREADS, smem, h->stream>>>(act2, act3, h->d_params, h->spec.off[6], wb3, n, H2, W2, p2, p2, tc_err_flag(h));
     else
       stem::stem3_tc_kernel<1><<<grid, stem::THREADS, smem, h->stream>>>(act2, act3, h->d_params, h->spec.off[6], wb3, n, H2, W2, p2, p2, tc_err_flag(h));

@@ -438,15 +438,16 @@ stem_fused_kernel(const TIn* __restrict__ img, float4* __restrict__ act3, const 
 #pragma unroll
             for (int c = 0; c < 12; ++c) o[c] = fmaxf(__uint_as_float(v[c]) + S.b3[12 * ch + c], 0.f);
             if constexpr (OUT_MODE == 2) {
-              // bf16 planes hold 8 channels: channels 0..11 = plane 0 + low half of plane 1, 12..23 = high half + plane 2
+              const bool f16 = S.b3[tc::F16_FLAG_SLOT] != 0.f;
+              // 16-bit planes hold 8 channels: channels 0..11 = plane 0 + low half of plane 1, 12..23 = high half + plane 2
               uint4* dst = reinterpret_cast<uint4*>(act3) + (((size_t)n * H4 + y3) * tc::NG_BF16) * (size_t)(W4 + 2 * UBD_MAP_PAD) + UBD_MAP_PAD + x3;
               const size_t ps = (size_t)(W4 + 2 * UBD_MAP_PAD);
               if (ch == 0) {
-                dst[0] = make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
-                *reinterpret_cast<uint2*>(dst + ps) = make_uint2(tc::pack_bf16x2(o[8], o[9]), tc::pack_bf16x2(o[10], o[11]));
+                dst[0] = make_uint4(tc::pack16(o[0], o[1], f16), tc::pack16(o[2], o[3], f16), tc::pack16(o[4], o[5], f16), tc::pack16(o[6], o[7], f16));
+                *reinterpret_cast<uint2*>(dst + ps) = make_uint2(tc::pack16(o[8], o[9], f16), tc::pack16(o[10], o[11], f16));
               } else {
-                *(reinterpret_cast<uint2*>(dst + ps) + 1) = make_uint2(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]));
-                dst[2 * ps] = make_uint4(tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]), tc::pack_bf16x2(o[8], o[9]), tc::pack_bf16x2(o[10], o[11]));
+                *(reinterpret_cast<uint2*>(dst + ps) + 1) = make_uint2(tc::pack16(o[0], o[1], f16), tc::pack16(o[2], o[3], f16));
+                dst[2 * ps] = make_uint4(tc::pack16(o[4], o[5], f16), tc::pack16(o[6], o[7], f16), tc::pack16(o[8], o[9], f16), tc::pack16(o[10], o[11], f16));
               }
             } else {
 #pragma unroll
@@ -489,7 +490,7 @@ static int stemf_launch(ubd_handle h, const void* d_img, int in_dtype, int prepr
   const uint8_t* wb3 = wb2 + stem::PW_WB_BYTES;
   int* counter = reinterpret_cast<int*>((uint8_t*)h->stem_wimg.p + 2 * stem::PW_WB_BYTES);
   UBD_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
-  const bool bf16 = h->precision == UBD_BF16;
+  const bool bf16 = ubd_is16(h);
 #define UBD_STEMF_LAUNCH(T, M, LUT, PS, PSH)                                                                                   \
   stemf::stem_fused_kernel<T, M><<<grid, stemf::THREADS, smem, h->stream>>>(                                                  \
       (const T*)d_img, act3, h->d_params, h->spec.off[0], h->spec.off[1], h->spec.off[2], h->spec.off[3], h->spec.off[6], wb2, \

@@ -133,12 +133,12 @@ constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((UMMA_N >>
 
 // kind::f16 with bf16 operands, fp32 accumulate, K-major A and B, M = 128, N = 32.
 constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((UMMA_N >> 3) << 17) | ((SEG >> 4) << 24);
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc = IDESC_BF16) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_BF16), "r"(accumulate), "r"(0u) : "memory");
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -184,6 +184,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// The 16-bit paths serve two containers: bf16 (precision UBD_BF16) and IEEE half (UBD_F16: the 10-bit significand of
+// tf32 in 16 bits, so maps cost half the traffic and an MMA consumes K = 16).  Which one a launch uses travels in the
+// weight blob: the last float of its 32-float bias block (channels 24..31 are padding) is non-zero for half.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));     // saturates at 65504: no inf * 0 in an MMA
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+constexpr int F16_FLAG_SLOT = 31;
 
 // in/out: padded row-interleaved maps (pad = PAD) of n_imgs images, in 16-byte units: tf32 maps have
 // 6 planes of float4, bf16 maps 3 planes of 8 x bf16.  wb: this layer's B image followed by bias[32];
@@ -293,6 +303,10 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
     // ------------------------------------------------------------------ MMA issuers (even / odd segments)
     const uint32_t parity = warp == 6 ? 1u : 0u;
     bool ok = mbar_wait(smem_u32(&S.wbar), 0, abort_flag, gerr, 2);
+    // 16-bit operands: bf16 or IEEE half (flag in the weight blob), fp32 accumulate
+    const bool f16 = BF16 && ok && reinterpret_cast<const float*>(S.wimg + W_BYTES_BF16)[F16_FLAG_SLOT] != 0.f;
+    const uint32_t idesc16 = f16 ? (IDESC_BF16 & ~((7u << 7) | (7u << 10))) : IDESC_BF16;
+    (void)idesc16;
     const uint32_t b_lo0 = ((smem_u32(S.wimg) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);      // LBO = 512 B
     const uint32_t a_lbo = ((plane_bytes >> 4) & 0x3FFFu) << 16;
     // per-tap column offsets in 16-byte units: (PAD + dx*d) pixels, + K-pair (two planes)
@@ -358,7 +372,7 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
               for (int tap = 0; tap < 9; ++tap) {                 // planes 0 + 1 of every tap
                 const int dy = tap / 3;
                 umma_bf16(tmem_d, make_desc(a_row[dy] + (uint32_t)(s * SEG) + tap_off[tap % 3], DESC_HI),
-                          make_desc(b_lo0 + tap * (B_TILE_BYTES >> 4), DESC_HI), tap != 0);
+                          make_desc(b_lo0 + tap * (B_TILE_BYTES >> 4), DESC_HI), tap != 0, idesc16);
               }
 #pragma unroll
               for (int dy = 0; dy < 3; ++dy) {
@@ -366,11 +380,11 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
                 // dilated: dx = -1, 0 (LBO = d pixels); stride-2: tj = 0, 2 (same parity array, LBO = 1 pixel)
                 const uint32_t a2 = (a_row[dy] & lbo_mask) + 2 * plane_units + (uint32_t)(s * SEG);
                 umma_bf16(tmem_d, make_desc((a2 + pair_off) | (pair_lbo << 16), DESC_HI),
-                          make_desc(b_lo0 + (9 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u);
+                          make_desc(b_lo0 + (9 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u, idesc16);
                 // plane 2 of the remaining tap; the B image's second K core is zero and LBO = 0 makes the A
                 // side re-read the same (finite) core instead of whatever lies beyond the slot
                 umma_bf16(tmem_d, make_desc(a2 + single_off, DESC_HI),
-                          make_desc(b_lo0 + (12 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u);
+                          make_desc(b_lo0 + (12 + dy) * (B_TILE_BYTES >> 4), DESC_HI), 1u, idesc16);
               }
             }
             umma_commit(smem_u32(&S.tfull[acc]));
@@ -389,6 +403,8 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
 #pragma unroll
     for (int c = 0; c < UBD_NF; ++c)
       bias[c] = ok ? reinterpret_cast<const float*>(S.wimg + (BF16 ? W_BYTES_BF16 : W_BYTES))[c] : 0.f;
+    const bool f16 = BF16 && ok && reinterpret_cast<const float*>(S.wimg + W_BYTES_BF16)[F16_FLAG_SLOT] != 0.f;
+    (void)f16;
     uint32_t it_rows_plus2 = 0;
     if (out_mode == 2) {
       const int et = (int)threadIdx.x - 64;                  // 0..127 over the four epilogue warps
@@ -456,8 +472,8 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
               if constexpr (BF16) {
 #pragma unroll
                 for (int g = 0; g < NG_BF16; ++g)
-                  o_px[(size_t)g * wps] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                                                     pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+                  o_px[(size_t)g * wps] = make_uint4(pack16(o[8 * g], o[8 * g + 1], f16), pack16(o[8 * g + 2], o[8 * g + 3], f16),
+                                                     pack16(o[8 * g + 4], o[8 * g + 5], f16), pack16(o[8 * g + 6], o[8 * g + 7], f16));
               } else {
 #pragma unroll
                 for (int g = 0; g < UBD_NG; ++g) {
@@ -469,8 +485,8 @@ dilconv_tc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const u
               uint4* o_px = out + (((size_t)it.n * h + y) * NG_BF16) * wpo + out_pad + x;
 #pragma unroll
               for (int g = 0; g < NG_BF16; ++g)
-                o_px[(size_t)g * wpo] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                                                  pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+                o_px[(size_t)g * wpo] = make_uint4(pack16(o[8 * g], o[8 * g + 1], f16), pack16(o[8 * g + 2], o[8 * g + 3], f16),
+                                                  pack16(o[8 * g + 4], o[8 * g + 5], f16), pack16(o[8 * g + 6], o[8 * g + 7], f16));
             } else {
               uint4* o_px = out + (((size_t)it.n * h + y) * UBD_NG) * wpo + out_pad + x;
               const bool rnd = !BF16 && out_mode == 0;
@@ -528,7 +544,7 @@ __global__ void merge_sep_kernel(const float* __restrict__ dw, const float* __re
 // 0..8 = tap t, ic 0..15; 9..11 = row dy: core0 = tap (dy,-1) ic 16..23, core1 = tap (dy,0) ic 16..23;
 // 12..14 = row dy: core0 = tap (dy,+1) ic 16..23, core1 = 0.  Then the fp32 bias.
 __global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
-                                       const int64_t* __restrict__ boff, uint8_t* __restrict__ wimg_all, int s2_pairing) {
+                                       const int64_t* __restrict__ boff, uint8_t* __restrict__ wimg_all, int s2_pairing, int f16) {
   const int layer = blockIdx.x;
   const float* K = params + koff[layer];
   const float* B = params + boff[layer];
@@ -542,10 +558,10 @@ __global__ void build_wimg_bf16_kernel(const float* __restrict__ params, const i
     else if (m < 12) { tap = (m - 9) * 3 + (s2_pairing ? 2 * kcore : kcore); ic = 16 + col; }   // cores 0,1 = dx -1,0 | tj 0,2
     else if (kcore == 0) { tap = (m - 12) * 3 + (s2_pairing ? 1 : 2); ic = 16 + col; }          // dx = +1 | tj = 1
     const float v = (tap >= 0 && oc < UBD_NF) ? K[(tap * UBD_NF + ic) * UBD_NF + oc] : 0.f;
-    dst[i] = __float2bfloat16_rn(v);
+    if (f16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v); else dst[i] = __float2bfloat16_rn(v);
   }
   float* bias = reinterpret_cast<float*>(wimg_all + (size_t)layer * WB_BYTES_BF16 + W_BYTES_BF16);
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) bias[i] = i < UBD_NF ? B[i] : 0.f;
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) bias[i] = i < UBD_NF ? B[i] : (i == F16_FLAG_SLOT && f16 ? 1.f : 0.f);
 }
 
 }  // namespace tc
@@ -578,6 +594,7 @@ static int tc_prepare(ubd_handle h) {
     UBD_CUDA(cudaMemsetAsync(h->tc_weights.p, 0, total, h->stream));
     h->tc_weights_dirty = true;
   }
+  if (ubd_is16(h) && h->tc_w16 != h->precision) h->tc_weights_dirty = true;
   if (h->tc_weights_dirty) {
     int64_t offs[14];
     for (int l = 0; l < 6; ++l) { offs[l] = h->spec.off[9 + 2 * l]; offs[6 + l] = h->spec.off[10 + 2 * l]; }
@@ -586,7 +603,8 @@ static int tc_prepare(ubd_handle h) {
     UBD_CUDA(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, h->stream));
     UBD_CUDA(cudaStreamSynchronize(h->stream));      // offs is a stack array
     tc::build_wimg_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p);
-    tc::build_wimg_bf16_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p + kTcImgTf32, 0);
+    const int f16 = h->precision == UBD_F16;
+    tc::build_wimg_bf16_kernel<<<6, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc_weights.p + kTcImgTf32, 0, f16);
     // L2 (separable 24->24) as one dense 3x3 kernel: K[tap][c][o] = dw2[tap][c] * pw2[c][o], bias b2
     ENSURE_RAW(h->l2dense, 2 * (9 * UBD_NF * UBD_NF + 32) * sizeof(float));
     tc::merge_sep_kernel<<<1, 256, 0, h->stream>>>(h->d_params + h->spec.off[3], h->d_params + h->spec.off[4], h->d_params + h->spec.off[5],
@@ -594,17 +612,18 @@ static int tc_prepare(ubd_handle h) {
     tc::build_wimg_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
                                                     (uint8_t*)h->tc_weights.p + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES);
     tc::build_wimg_bf16_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
-                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16, 0);
+                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)UBD_NLAYERS_DIL * tc::WB_BYTES_BF16, 0, f16);
     // L3 (separable 24->24, stride 2) likewise, image index 7
     float* l3 = (float*)h->l2dense.p + (9 * UBD_NF * UBD_NF + 32);
     tc::merge_sep_kernel<<<1, 256, 0, h->stream>>>(h->d_params + h->spec.off[6], h->d_params + h->spec.off[7], h->d_params + h->spec.off[8], l3);
     tc::build_wimg_kernel<<<1, 256, 0, h->stream>>>(l3, d_offs + 12, d_offs + 13,
                                                     (uint8_t*)h->tc_weights.p + (size_t)(UBD_NLAYERS_DIL + 1) * tc::WB_BYTES);
     tc::build_wimg_bf16_kernel<<<1, 256, 0, h->stream>>>(l3, d_offs + 12, d_offs + 13,
-                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)(UBD_NLAYERS_DIL + 1) * tc::WB_BYTES_BF16, 1);
+                                                         (uint8_t*)h->tc_weights.p + kTcImgTf32 + (size_t)(UBD_NLAYERS_DIL + 1) * tc::WB_BYTES_BF16, 1, f16);
     h->launches += 8;
     UBD_CUDA(cudaGetLastError());
     h->tc_weights_dirty = false;
+    h->tc_w16 = ubd_is16(h) ? h->precision : h->tc_w16;
   }
   return UBD_OK;
 }
@@ -618,10 +637,10 @@ static inline int* tc_err_flag(ubd_handle h) {
 // L3 as a merged dense stride-2 kernel (s2 = 1: FML padding, 2: none).
 static int tc_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
                              int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr, int s2 = 0) {
-  if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
+  if (h->precision == UBD_FP32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32, bf16 or f16");
   int rc = tc_prepare(h);
   if (rc) return rc;
-  const bool bf16 = h->precision == UBD_BF16;
+  const bool bf16 = ubd_is16(h);
   const uint8_t* base = (const uint8_t*)h->tc_weights.p;
   const uint8_t* wb = bf16 ? base + kTcImgTf32 + (size_t)layer * tc::WB_BYTES_BF16 : base + (size_t)layer * tc::WB_BYTES;
   const uint8_t* zeros = base + kTcZeroOff;

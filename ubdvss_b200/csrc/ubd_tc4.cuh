@@ -39,7 +39,7 @@ namespace tc4 {
 
 using tc::smem_u32; using tc::elect_one; using tc::mbar_init; using tc::mbar_arrive; using tc::mbar_expect_tx;
 using tc::mbar_wait; using tc::bulk_g2s; using tc::umma_commit; using tc::tc_fence_before; using tc::tc_fence_after;
-using tc::make_desc; using tc::round_tf32; using tc::pack_bf16x2; using tc::HeadArgs;
+using tc::make_desc; using tc::round_tf32; using tc::pack_bf16x2; using tc::pack16; using tc::HeadArgs;
 
 // Bounded wait like tc::mbar_wait; on a stall every warp leaves (code << 24 | info) in gerr[1 + warp].
 __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code, uint32_t info) {
@@ -216,6 +216,9 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
     if (layer > 0) in = pipe.ring + (size_t)(layer - 1) * pipe.ring_imgs * pipe.img_units;
     out = pipe.ring + (size_t)layer * pipe.ring_imgs * pipe.img_units;
   }
+  // 16-bit maps: bf16 or IEEE half (flag in the weight blob, tc::F16_FLAG_SLOT)
+  const bool f16 = BF16 && __ldg(reinterpret_cast<const float*>(wb + (BF16 ? W_BYTES_BF16 : W_BYTES_TF32)) + tc::F16_FLAG_SLOT) != 0.f;
+  (void)f16;
   const int n_outer = PIPE ? n_imgs : 1;                     // PIPE: the roles walk image by image
   auto make_walk = [&](int m) { return PIPE ? Walk(1, h, w, d, sw, (kidx + m) % K, K) : Walk(n_imgs, h, w, d, sw, kidx, K); };
   constexpr int NS = S_t::NS;
@@ -357,7 +360,7 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
     const uint32_t plane_units = plane_bytes >> 4;
     const uint32_t a_lbo = (plane_units & 0x3FFFu) << 16;
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-    const uint32_t idesc0 = BF16 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24))
+    const uint32_t idesc0 = BF16 ? ((1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((128u >> 4) << 24))
                                  : ((1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24));
     const uint32_t tmem_t = tmem_base + (uint32_t)seg * 128u;
     uint32_t lseq = 0, par_e = 0;
@@ -498,8 +501,8 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             if constexpr (BF16) {
 #pragma unroll
               for (int g = 0; g < 3; ++g)
-                o_px[(size_t)g * wps] = make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
-                                                   pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7]));
+                o_px[(size_t)g * wps] = make_uint4(pack16(a[8 * g], a[8 * g + 1], f16), pack16(a[8 * g + 2], a[8 * g + 3], f16),
+                                                   pack16(a[8 * g + 4], a[8 * g + 5], f16), pack16(a[8 * g + 6], a[8 * g + 7], f16));
             } else {
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g) {
@@ -512,8 +515,8 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             uint4* o_px = out + (((size_t)out_n * h + y) * 3) * wpo + out_pad + x;
 #pragma unroll
             for (int g = 0; g < 3; ++g)
-              __stcs(o_px + (size_t)g * wpo, make_uint4(pack_bf16x2(a[8 * g], a[8 * g + 1]), pack_bf16x2(a[8 * g + 2], a[8 * g + 3]),
-                                                        pack_bf16x2(a[8 * g + 4], a[8 * g + 5]), pack_bf16x2(a[8 * g + 6], a[8 * g + 7])));
+              __stcs(o_px + (size_t)g * wpo, make_uint4(pack16(a[8 * g], a[8 * g + 1], f16), pack16(a[8 * g + 2], a[8 * g + 3], f16),
+                                                        pack16(a[8 * g + 4], a[8 * g + 5], f16), pack16(a[8 * g + 6], a[8 * g + 7], f16)));
           } else {
             uint4* o_px = out + (((size_t)out_n * h + y) * UBD_NG) * wpo + out_pad + x;
             const bool rnd = !BF16 && out_mode == 0;
@@ -639,8 +642,8 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
 #pragma unroll
               for (int g = 0; g < 3; ++g)
                 *reinterpret_cast<uint4*>(px + g * plane_bytes) =
-                    make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                               pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+                    make_uint4(pack16(o[8 * g], o[8 * g + 1], f16), pack16(o[8 * g + 2], o[8 * g + 3], f16),
+                               pack16(o[8 * g + 4], o[8 * g + 5], f16), pack16(o[8 * g + 6], o[8 * g + 7], f16));
             } else {
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g)
@@ -701,7 +704,7 @@ __global__ void build_img_tf32_kernel(const float* __restrict__ params, const in
 // bf16: images 0..2 = tap dx, ic 0..15; image 3 = K core 0: tap dx=-1, K core 1: tap dx=0, ic 16..23;
 // image 4 = K core 0: tap dx=+1, ic 16..23, K core 1 zero; image 5 = image 0 without ky0.
 __global__ void build_img_bf16_kernel(const float* __restrict__ params, const int64_t* __restrict__ koff,
-                                      const int64_t* __restrict__ boff, uint8_t* __restrict__ dst_all) {
+                                      const int64_t* __restrict__ boff, uint8_t* __restrict__ dst_all, int f16) {
   const int layer = blockIdx.x;
   const float* K = params + koff[layer];
   const float* B = params + boff[layer];
@@ -720,10 +723,10 @@ __global__ void build_img_bf16_kernel(const float* __restrict__ params, const in
     else if (m == 3) { dx = kcore; ic = 16 + col; }
     else if (kcore == 0) { dx = 2; ic = 16 + col; }
     const float v = (ky >= 0 && dx >= 0 && oc < UBD_NF) ? K[((ky * 3 + dx) * UBD_NF + ic) * UBD_NF + oc] : 0.f;
-    dst[i] = __float2bfloat16_rn(v);
+    if (f16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v); else dst[i] = __float2bfloat16_rn(v);
   }
   float* bias = reinterpret_cast<float*>(dst_all + (size_t)layer * WB_BYTES_BF16 + W_BYTES_BF16);
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) bias[i] = i < UBD_NF ? B[i] : 0.f;
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) bias[i] = i < UBD_NF ? B[i] : (i == tc::F16_FLAG_SLOT && f16 ? 1.f : 0.f);
 }
 
 }  // namespace tc4
@@ -750,18 +753,20 @@ static int tc4_prepare(ubd_handle h) {
     h->tc4_weights.cap = kTc4Tf32 + kTc4Bf16;
     h->tc4_weights_dirty = true;
   }
+  if (ubd_is16(h) && h->tc4_w16 != h->precision) h->tc4_weights_dirty = true;
   if (h->tc4_weights_dirty) {
     const int64_t* d_offs = reinterpret_cast<const int64_t*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES + 64);
     tc4::build_img_tf32_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p);
-    tc4::build_img_bf16_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p + kTc4Tf32);
+    tc4::build_img_bf16_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p + kTc4Tf32, h->precision == UBD_F16);
     // image 6: the stem's L2 (separable 24->24) as one dense 3x3 kernel, merged by tc_prepare into h->l2dense
     tc4::build_img_tf32_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
                                                          (uint8_t*)h->tc4_weights.p + (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_TF32);
     tc4::build_img_bf16_kernel<<<1, 256, 0, h->stream>>>((const float*)h->l2dense.p, d_offs + 12, d_offs + 13,
-                                                         (uint8_t*)h->tc4_weights.p + kTc4Tf32 + (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_BF16);
+                                                         (uint8_t*)h->tc4_weights.p + kTc4Tf32 + (size_t)UBD_NLAYERS_DIL * tc4::WB_BYTES_BF16, h->precision == UBD_F16);
     h->launches += 4;
     UBD_CUDA(cudaGetLastError());
     h->tc4_weights_dirty = false;
+    h->tc4_w16 = ubd_is16(h) ? h->precision : h->tc4_w16;
   }
   return UBD_OK;
 }
@@ -771,10 +776,10 @@ static int tc4_prepare(ubd_handle h) {
 static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
                               int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr,
                               const tc::L1Args* l1 = nullptr) {
-  if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
+  if (h->precision == UBD_FP32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32, bf16 or f16");
   int rc = tc4_prepare(h);
   if (rc) return rc;
-  const bool bf16 = h->precision == UBD_BF16;
+  const bool bf16 = ubd_is16(h);
   const uint8_t* base = (const uint8_t*)h->tc4_weights.p;
   const uint8_t* wb = bf16 ? base + kTc4Tf32 + (size_t)layer * tc4::WB_BYTES_BF16 : base + (size_t)layer * tc4::WB_BYTES_TF32;
   const int sw = ww <= tc4::SW_MAX ? ww : tc4::SW_MAX;
@@ -802,10 +807,10 @@ static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer
 // DRAM traffic 2.6 GB against 4.2 GB: a group of 25 CTAs splits an image into 10-row pieces, whose two halo rows each cost
 // a fifth of the staging and tensor work, and 106 MB of rings do not stay resident in the 126 MB L2 (hit rate 41 %).
 static int tc4_launch_pipeline(ubd_handle h, const void* in, int n, int hh, int ww, const tc::HeadArgs* head) {
-  if (h->precision != UBD_TF32 && h->precision != UBD_BF16) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32 or bf16");
+  if (h->precision == UBD_FP32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32, bf16 or f16");
   int rc = tc4_prepare(h);
   if (rc) return rc;
-  const bool bf16 = h->precision == UBD_BF16;
+  const bool bf16 = ubd_is16(h);
   const int ring = std::max(2, h->opt_pipe_ring);
   const size_t img_units = act_elems(1, hh, ww, UBD_MAP_PAD) / (bf16 ? 2 : 1);               // 16-byte units per map
   const size_t ring_bytes = (size_t)(UBD_NLAYERS_DIL - 1) * ring * img_units * 16;

@@ -252,7 +252,7 @@ class Engine:
         check(self._h, self._lib.ubd_prepare_images(self._h, ptr(x), n, H, W, c, int(out_h), int(out_w), int(bool(to_grey)), ptr(out)))
         return out
 
-    # ---------------------------------------------------------------- pipelined inference (two batches in flight)
+    # ---------------------------------------------------------------- pipelined inference (up to three batches in flight)
     def segment_submit(self, images, logit_thr: float, min_area_x2: int, preproc: int = _lib.PREPROC_NONE,
                        mask_out=None, logits_out=None, max_comps: int = 0, device_ptr: int = 0, shape=None, dtype=None):
         """Queue one batch and return a ticket object for ``segment_wait``.  ``images``: host array (pass pinned memory

@@ -48,7 +48,7 @@ class ModelRunner:
 
     def predict_stream(self, model, batches, rescale=False, preprocessing=None):
         """The per-batch loop of ``ModelRunner.run`` (model_runner.py:40-103: ``next(generator)`` -> ``predict`` ->
-        consume) with two batches in flight: while batch k runs on the GPU, batch k+1 is being copied and batch
+        consume) with up to three batches in flight: while batch k runs on the GPU, batches k+1, k+2 are being copied and batch
         k-1's boxes are finished on the host.  ``batches`` yields ``images`` or ``(images, meta_infos)``; yields
         exactly what ``predict`` returns for each batch, in order, with identical values."""
         cfg = self._net_config
@@ -73,7 +73,7 @@ class ModelRunner:
             images, metas = item if isinstance(item, tuple) else (item, None)
             assert not rescale or (metas is not None and len(images) == len(metas))
             pending.append((model.segment_submit(images, thr32, ma2, preprocessing=preprocessing), metas))
-            if len(pending) == 2:
+            if len(pending) == 3:
                 yield finish(pending.pop(0))
         while pending:
             yield finish(pending.pop(0))

@@ -210,7 +210,7 @@ class B200Model:
         return mask, logits, comps, counts
 
     def segment_submit(self, images, logit_thr, min_area_x2, preprocessing=None):
-        """Queue one batch (two may be in flight); see ``ModelRunner.predict_stream``."""
+        """Queue one batch (three may be in flight); see ``ModelRunner.predict_stream``."""
         x = np.asarray(images)
         n, H, W = x.shape[:3]
         mask = np.empty((n, H // 4, W // 4), np.uint8)
