@@ -205,6 +205,11 @@ int64_t ubd_launch_count(ubd_handle h);
  * weights and dilation) on a host NHWC (n,mh,mw,24) map through the FP32 or the tcgen05 kernel. */
 int ubd_debug_dilated_layer(ubd_handle h, const float* in_nhwc, float* out_nhwc, int layer,
                             int n, int mh, int mw, int precision);
+/* Debug: weight and bias gradient of one dilated 3x3 layer on the tensor cores (the K = pixels GEMM of the training
+ * step, ubd_wgrad.cuh): x = the layer's input map, g = the gradient at its output, both (n,h,w,24) fp32 NHWC;
+ * dK = (3,3,24,24) HWIO, dB = (24). */
+int ubd_debug_wgrad(ubd_handle h, const float* x_nhwc, const float* g_nhwc, int n, int height, int width,
+                    int dilation, float* dK, float* dB);
 
 /* Tuning hook: with option "tc_trace" = 1 the tcgen05 kernel records cycle stamps of CTA 0
  * ([3 roles][1024 events][4 stamps], int64); this reads and clears them. */

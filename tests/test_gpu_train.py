@@ -183,3 +183,93 @@ def test_native_nccl_exchange_world_of_one():
     assert all(np.array_equal(a, b) for a, b in zip(g0, g1))
     eng.adam_step()
     assert any(not np.array_equal(a, b) for a, b in zip(w, eng.get_weights()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core training path (a tf32 handle): dilated layers forward / data gradient / weight gradient on tcgen05
+# ---------------------------------------------------------------------------------------------------------------
+
+def _wgrad_ref(x, g, d):
+    """dK[ky][kx][ic][oc] = sum_px x[y + (ky-1)d][x + (kx-1)d][ic] g[y][x][oc] in float64 (zero padding), dB = sum_px g."""
+    n, h, w, _ = x.shape
+    xp = np.zeros((n, h + 2 * d, w + 2 * d, 24), np.float64)
+    xp[:, d:d + h, d:d + w] = x
+    dk = np.zeros((3, 3, 24, 24), np.float64)
+    for ky in range(3):
+        for kx in range(3):
+            dk[ky, kx] = np.einsum("nyxi,nyxo->io", xp[:, ky * d:ky * d + h, kx * d:kx * d + w], g.astype(np.float64))
+    return dk, g.astype(np.float64).sum((0, 1, 2))
+
+
+@pytest.mark.parametrize("d", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("shape", [(2, 32, 128), (1, 8, 8), (3, 20, 36), (1, 40, 260), (5, 64, 64), (1, 3, 12)])
+def test_wgrad_tcgen05_matches_numpy(d, shape):
+    """ubd_wgrad.cuh: the K = pixels GEMM with both operands MN-major straight from the staged map rows.  Inputs on the
+    tf32 grid, so only the fp32 accumulation order differs from the float64 reference; ragged widths (not a multiple of
+    the 8-pixel K step), several strips per row (w > 128), maps smaller than the dilation, more CTAs than rows."""
+    rng = np.random.default_rng(d * 100 + shape[2])
+    x = onet.round_tf32(np.maximum(rng.normal(0, 1, size=shape + (24,)), 0).astype(np.float32))
+    g = onet.round_tf32((rng.normal(0, 1, size=shape + (24,)) * (rng.random(shape + (24,)) < 0.7)).astype(np.float32))
+    eng = _engine(precision="tf32")
+    eng.set_weights(onet.init_weights(0, seed=1))
+    dk, db = eng.debug_wgrad(x, g, d)
+    rk, rb = _wgrad_ref(x, g, d)
+    scale = np.sqrt(shape[0] * shape[1] * shape[2])
+    assert np.abs(dk - rk).max() <= 1e-5 * scale + 1e-6 * np.abs(rk).max(), (np.abs(dk - rk).max(), np.abs(rk).max())
+    assert np.abs(db - rb).max() <= 1e-5 * scale + 1e-6 * np.abs(rb).max()
+    dk2, db2 = eng.debug_wgrad(x, g, d)
+    assert np.array_equal(dk, dk2) and np.array_equal(db, db2)          # fixed summation order
+
+
+@pytest.mark.parametrize("n_classes,shape", [(0, (2, 64, 96)), (4, (3, 48, 80)), (0, (2, 128, 640)), (0, (1, 80, 1040))])
+def test_tensor_core_training_step_matches_oracle(n_classes, shape):
+    """The tf32 handle's training step against the autograd oracle (float32 torch-CPU) and against the library's exact
+    FP32 path: tf32 operands (10-bit significands) in the six dilated layers' forward, dgrad and wgrad."""
+    w = onet.init_weights(n_classes, seed=3)
+    n, H, W = shape
+    x = synth.synth_images(n, H, W, seed=3)
+    y = synth.synth_targets(n, H // 4, W // 4, n_classes, seed=3)
+    xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
+    loss, _, ref_grads, _ = L.train_step_torch(w, xf, y, n_classes > 0)
+    eng = _engine(n_classes=n_classes, precision="tf32")
+    eng.set_weights(w)
+    parts = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    grads = eng.get_grads()
+    assert abs(parts[0] - loss) <= 5e-3 * max(1.0, abs(loss)), (parts, loss)
+    for i, (g, r) in enumerate(zip(grads, ref_grads)):
+        err = np.abs(g - r).max()
+        assert err <= 1e-6 + 5e-2 * np.abs(r).max(), (i, err, np.abs(r).max())
+        assert np.linalg.norm((g - r).ravel()) <= 1e-6 + 3e-2 * np.linalg.norm(r.ravel()), i
+    # option train_tc 0 = the exact FP32 path on the same handle
+    eng.set_option("train_tc", 0)
+    p32 = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    assert abs(p32[0] - loss) <= 1e-4 * max(1.0, abs(loss))
+    for g, r in zip(eng.get_grads(), ref_grads):
+        assert np.abs(g - r).max() <= 1e-6 + 2e-3 * np.abs(r).max()
+
+
+def test_tensor_core_training_full_size_reproducible_and_learns():
+    """Config E (32 x 512x512) on the tf32 handle: finite, bit-reproducible, and Adam steps reduce the loss."""
+    w = synth.synth_weights(0, seed=1234, calibrated=True)
+    eng = _engine(precision="tf32")
+    eng.set_weights(w)
+    x = np.concatenate([synth.synth_images(8, 512, 512, seed=4)] * 4)
+    y = np.concatenate([synth.synth_targets(8, 128, 128, 0, seed=4)] * 4)
+    p1 = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    g1 = eng.get_grads()
+    p2 = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    g2 = eng.get_grads()
+    assert np.isfinite(p1).all() and np.array_equal(p1, p2)
+    for a, b in zip(g1, g2):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+    e32 = _engine()
+    e32.set_weights(w)
+    p32 = e32.train_step(x, y, _lib.PREPROC_MOBILENET)
+    assert abs(p32[0] - p1[0]) <= 5e-3 * abs(p32[0])
+    for a, b in zip(g1, e32.get_grads()):
+        assert np.linalg.norm((a - b).ravel()) <= 2e-2 * np.linalg.norm(b.ravel()) + 1e-7
+    losses = [p1[0]]
+    for _ in range(5):
+        eng.adam_step(lr=2e-3)
+        losses.append(eng.train_step(x, y, _lib.PREPROC_MOBILENET)[0])
+    assert losses[-1] < losses[0]

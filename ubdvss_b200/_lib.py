@@ -69,6 +69,7 @@ SIGNATURES = {
     "ubd_allreduce_grads": (_i, [_vp]),
     "ubd_comm_destroy": (_i, [_vp]),
     "ubd_debug_dilated_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),
+    "ubd_debug_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ubd_debug_read_trace": (_i, [_vp, _vp, _i]),
     "ubd_synchronize": (_i, [_vp]),
     "ubd_set_stream": (_i, [_vp, _vp]),

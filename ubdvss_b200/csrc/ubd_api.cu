@@ -21,6 +21,7 @@
 #include "ubd_stem_tc.cuh"
 #include "ubd_stemf.cuh"
 #include "ubd_train.cuh"
+#include "ubd_wgrad.cuh"
 
 static std::string g_create_error;
 
@@ -231,6 +232,8 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   else if (!strcmp(name, "tc_variant")) h->opt_tc_variant = (int)value;
   else if (!strcmp(name, "pipeline")) h->opt_pipeline = value != 0;
   else if (!strcmp(name, "cc_stream")) h->opt_cc_stream = value != 0;
+  else if (!strcmp(name, "train_tc")) h->opt_train_tc = value != 0;
+  else if (!strcmp(name, "train_tc_bits")) h->opt_train_tc_bits = (int)value;
   else if (!strcmp(name, "pipe_ring")) { if (value < 2) UBD_FAIL(UBD_ERR_ARG, "pipe_ring must be >= 2"); h->opt_pipe_ring = (int)value; }
   else if (!strcmp(name, "stem_chunk")) h->opt_stem_chunk = (int)value;
   else if (!strcmp(name, "tc_trace")) {
@@ -240,7 +243,7 @@ extern "C" int ubd_set_option(ubd_handle h, const char* name, int64_t value) {
   else if (!strcmp(name, "precision")) {
     if (value < UBD_FP32 || value > UBD_F16) UBD_FAIL(UBD_ERR_ARG, "bad precision");
     // the 16-bit weight images hold bf16 or half: rebuild them when the container changes
-    if ((int)value != h->precision) { h->tc_weights_dirty = h->tc4_weights_dirty = h->stem_weights_dirty = true; h->act2_tag = 0; }
+    if ((int)value != h->precision) { h->tc_weights_dirty = h->tc4_weights_dirty = h->tc4_train_dirty = h->stem_weights_dirty = true; h->act2_tag = 0; }
     h->precision = (int)value;
   }
   else UBD_FAIL(UBD_ERR_ARG, std::string("unknown option ") + name);
@@ -272,6 +275,7 @@ extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const i
   h->have_weights = true;
   h->tc_weights_dirty = true;
   h->tc4_weights_dirty = true;
+  h->tc4_train_dirty = true;
   h->stem_weights_dirty = true;
   return UBD_OK;
 }
@@ -311,21 +315,21 @@ static size_t image_bytes(ubd_handle h, int in_dtype, int n, int H, int W) {
 template <int CIN, int STRIDE, bool RAW, typename TIn>
 static int launch_sep(ubd_handle h, const TIn* in, float4* out, int layer, int n, int H, int W, int Ho, int Wo,
                       int pad_t, int pad_l, const float* lut, float pre_scale, float pre_shift,
-                      int in_mpad = 0, int out_mpad = 0) {
+                      int in_mpad = 0, int out_mpad = 0, float4* dwout = nullptr) {
   const float* base = h->d_params;
   const float* dwk = base + h->spec.off[3 * layer];
   const float* pwk = base + h->spec.off[3 * layer + 1];
   const float* b = base + h->spec.off[3 * layer + 2];
   dim3 grid((Wo + 31) / 32, (Ho + 3) / 4, n), block(128);
   sep_layer_kernel<CIN, STRIDE, RAW, TIn><<<grid, block, 0, h->stream>>>(in, out, dwk, pwk, b, lut, pre_scale, pre_shift,
-                                                                        n, H, W, Ho, Wo, pad_t, pad_l, in_mpad, out_mpad);
+                                                                        n, H, W, Ho, Wo, pad_t, pad_l, in_mpad, out_mpad, dwout);
   LAUNCH_CHECK();
   return UBD_OK;
 }
 
 
 static int run_stem(ubd_handle h, const void* d_img, int in_dtype, int preproc, int n, int H, int W,
-                    float4* act1, float4* act2, float4* act3) {
+                    float4* act1, float4* act2, float4* act3, float4* dw2 = nullptr, float4* dw3 = nullptr) {
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
   const int p2 = stride2_pad(h);
   const bool mob = preproc == UBD_PREPROC_MOBILENET;
@@ -342,12 +346,12 @@ static int run_stem(ubd_handle h, const void* d_img, int in_dtype, int preproc, 
       rc = launch_sep<3, 2, true, float>(h, (const float*)d_img, act1, 0, n, H, W, H2, W2, p2, p2, nullptr, mob ? 127.5f : 0.f, 127.5f);
   }
   if (rc) return rc;
-  rc = launch_sep<24, 1, false, float>(h, (const float*)act1, act2, 1, n, H2, W2, H2, W2, 1, 1, nullptr, 0.f, 0.f);
+  rc = launch_sep<24, 1, false, float>(h, (const float*)act1, act2, 1, n, H2, W2, H2, W2, 1, 1, nullptr, 0.f, 0.f, 0, 0, dw2);
   if (rc) return rc;
   // the tensor-core layers read tf32: round (rna) where the map is produced instead of letting the
   // MMA truncate it
   rc = launch_sep<24, 2, false, float>(h, (const float*)act2, act3, 2, n, H2, W2, H4, W4, p2, p2, nullptr,
-                                       h->precision == UBD_TF32 ? -1.f : 0.f, 0.f, 0, UBD_MAP_PAD);
+                                       h->precision == UBD_TF32 ? -1.f : 0.f, 0.f, 0, UBD_MAP_PAD, dw3);
   return rc;
 }
 

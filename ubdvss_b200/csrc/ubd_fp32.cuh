@@ -25,7 +25,8 @@ sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
                  const float* __restrict__ bias,  // [24]
                  const float* __restrict__ lut,   // RAW u8: 256-entry preprocessing table (or null)
                  float pre_scale, float pre_shift,
-                 int N, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int in_mpad, int out_mpad) {
+                 int N, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int in_mpad, int out_mpad,
+                 float4* __restrict__ dwout = nullptr) {   // training: keep the depthwise output (pad 0) for the pointwise wgrad
   __shared__ float s_dw[9 * CIN];
   __shared__ __align__(16) float s_pw[CIN * UBD_NF];
   __shared__ float s_b[UBD_NF];
@@ -82,6 +83,13 @@ sep_layer_kernel(const TIn* __restrict__ in, float4* __restrict__ out,
     }
   }
 
+  if constexpr (!RAW && CIN == UBD_NF) {
+    if (dwout != nullptr) {
+#pragma unroll
+      for (int g = 0; g < UBD_NG; ++g)
+        dwout[act_index(n, g, y, x, Ho, Wo, 0)] = make_float4(d[4 * g], d[4 * g + 1], d[4 * g + 2], d[4 * g + 3]);
+    }
+  }
   const float4* pw4 = reinterpret_cast<const float4*>(s_pw);
 #pragma unroll
   for (int og = 0; og < UBD_NG; ++og) {

@@ -55,6 +55,7 @@ struct ubd_handle_s {
   bool have_weights = false;
   bool tc_weights_dirty = true;   // tensor-core weight images must be rebuilt from d_params
   bool tc4_weights_dirty = true;  // ... the column-rotating kernel's weight images (ubd_tc4.cuh)
+  bool tc4_train_dirty = true;    // ... the six dilated tf32 images the training step needs (rebuilt alone between Adam steps)
   int tc_w16 = -1, tc4_w16 = -1, stem_w16 = -1;   // which 16-bit container (UBD_BF16 / UBD_F16) the built images hold
   int opt_pipeline = 0;           // dilated stack: 1 = one layer-pipelined launch with L2 ring buffers for chunks of >= 24 images
                                   // (measured 0.84 ms vs 0.83 ms per 64 x 1024^2 for one launch per layer, profiles/r02_summary.md)
@@ -87,6 +88,10 @@ struct ubd_handle_s {
   DevBuf tc_trace;                // optional event trace of CTA 0 (option "tc_trace")
   DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
   DevBuf tc4_weights;             // per-layer weight images of the column-rotating kernel (+ bias)
+  DevBuf tc4_bwd;                 // training: flipped kernels (HWIO) + zero bias + offsets, then their tf32 weight images
+  bool bwd_offs_ready = false;
+  int opt_train_tc_bits = 7;
+  bool opt_train_tc = true;       // training step of a tf32 handle runs its dilated layers (fwd, dgrad, wgrad) on tcgen05
   // training workspaces
   DevBuf t_acts, t_grads_act, t_scratch, t_partials, d_grads, d_adam_m, d_adam_v, d_ytrue, d_dlogits, t_loss, d_metric;
   int64_t adam_t = 0;
@@ -102,7 +107,7 @@ struct ubd_handle_s {
   std::vector<DevBuf*> all_bufs() {
     std::vector<DevBuf*> v = {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
             &cls_sums, &out_index, &row_ext, &run_label, &pipe_ring, &pipe_flags, &prep_tab, &prep_a, &prep_b, &prep_in, &prep_out,
-            &tc_weights, &tc4_weights, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
+            &tc_weights, &tc4_weights, &tc4_bwd, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
     for (ResultSlot& R : rs)
       for (DevBuf* b : {&R.hdr, &R.out_recs, &R.hull_pts, &R.box_recs, &R.d_images, &R.d_mask, &R.d_logits}) v.push_back(b);

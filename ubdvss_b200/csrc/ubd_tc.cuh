@@ -202,7 +202,8 @@ constexpr int F16_FLAG_SLOT = 31;
 //
 // out_mode 2: the 1x1 head (net.py:307-311) and the logit threshold (model_runner.py:124) run in the
 // epilogue: the thread that owns a pixel holds its 24 channels, so the last map never reaches HBM.
-struct HeadArgs { const float* hk; const float* hb; int n_out; float thr; float* logits; uint8_t* mask; };
+struct HeadArgs { const float* hk; const float* hb; int n_out; float thr; float* logits; uint8_t* mask;
+                  const uint4* gate; };   // out_mode 4 (ubd_tc4.cuh): map whose sign gates the output (ReLU derivative)
 // Arguments of the L1-producer variant of the column-rotating kernel (ubd_tc4.cuh): grey uint8 image -> L1 rows.
 struct L1Args { const float* lut; const float* dw1; const float* pw1; const float* b1; int H, W, pad_t, pad_l; };
 

@@ -193,6 +193,8 @@ __device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t adesc,
 // out_mode 0: same format as the input (tf32 rna / bf16), 1: fp32 6-plane unrounded, 2: fused 1x1 head +
 // logit threshold (net.py:307-311, model_runner.py:124): the last map never reaches HBM.
 // out_mode 3: parity-split output [n][y][x & 1][plane][PAD + (x >> 1)] (input of the stride-2 layer).
+// out_mode 5: as 0 (tf32 only), with the rounded-off mantissa bits cleared (training forward).
+// out_mode 4: no bias / ReLU; output gated by the sign of head.gate (backward-data pass of the training step, tf32).
 // L1SRC: `in` is the uint8 grey image, h / w the half-resolution map size, d = 1 (see tc::L1Args).
 template <bool BF16, bool L1SRC, bool PIPE = false>
 __global__ void __launch_bounds__(L1SRC ? THREADS_L1 : THREADS, 1)
@@ -482,8 +484,23 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
           const int x = pc.x0 + xs;
           float a[UBD_NF];
 #pragma unroll
-          for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
-          if (out_mode == 2) {
+          for (int c = 0; c < UBD_NF; ++c) a[c] = out_mode == 4 ? __uint_as_float(v[c]) : fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
+          if (out_mode == 4) {
+            // backward-data pass (training): the conv ran with the flipped kernel; gate by the ReLU of the layer below
+            // (its saved activation, same layout as the output) and leave the gradient on the tf32 grid for the next MMAs
+            if constexpr (!BF16) {
+              const size_t o_idx = (((size_t)out_n * h + y) * UBD_NG) * wpo + out_pad + x;
+#pragma unroll
+              for (int g = 0; g < UBD_NG; ++g) {
+                const uint4 gt = __ldg(head.gate + o_idx + (size_t)g * wpo);
+                float4 q = make_float4(__uint_as_float(gt.x) > 0.f ? rna_mma(a[4 * g]) : 0.f, __uint_as_float(gt.y) > 0.f ? rna_mma(a[4 * g + 1]) : 0.f,
+                                       __uint_as_float(gt.z) > 0.f ? rna_mma(a[4 * g + 2]) : 0.f, __uint_as_float(gt.w) > 0.f ? rna_mma(a[4 * g + 3]) : 0.f);
+                uint4 u = *reinterpret_cast<uint4*>(&q);
+                u.x &= 0xFFFFE000u; u.y &= 0xFFFFE000u; u.z &= 0xFFFFE000u; u.w &= 0xFFFFE000u;
+                out[o_idx + (size_t)g * wpo] = u;
+              }
+            }
+          } else if (out_mode == 2) {
             const size_t p = ((size_t)pc.n * h + y) * w + x;
             const float* hw = S.headw;
             float* lo = head.logits ? head.logits + p * head.n_out : nullptr;
@@ -519,12 +536,18 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
                                                         pack16(a[8 * g + 4], a[8 * g + 5], f16), pack16(a[8 * g + 6], a[8 * g + 7], f16)));
           } else {
             uint4* o_px = out + (((size_t)out_n * h + y) * UBD_NG) * wpo + out_pad + x;
-            const bool rnd = !BF16 && out_mode == 0;
+            const bool rnd = !BF16 && (out_mode == 0 || out_mode == 5);
 #pragma unroll
             for (int g = 0; g < UBD_NG; ++g) {
               float4 q = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
               if (rnd) { q.x = rna_mma(q.x); q.y = rna_mma(q.y); q.z = rna_mma(q.z); q.w = rna_mma(q.w); }
-              __stcs(o_px + (size_t)g * wpo, *reinterpret_cast<uint4*>(&q));
+              uint4 u = *reinterpret_cast<uint4*>(&q);
+              if (out_mode == 5) {
+                // training forward: the map is also read by FP32 code (ReLU gates test a > 0, the head, the weight gradient),
+                // so the low bits are really cleared - a clamped 0 must stay 0, not half a tf32 ulp
+                u.x &= 0xFFFFE000u; u.y &= 0xFFFFE000u; u.z &= 0xFFFFE000u; u.w &= 0xFFFFE000u;
+              }
+              __stcs(o_px + (size_t)g * wpo, u);
             }
           }
         }
@@ -771,17 +794,37 @@ static int tc4_prepare(ubd_handle h) {
   return UBD_OK;
 }
 
+// Training step: between two Adam updates only the six dilated tf32 images are needed (forward and, with flipped kernels,
+// backward-data launches).  Rebuild them alone and leave the full-rebuild flags set for the next inference call.
+static int tc4_prepare_train(ubd_handle h) {
+  if (!h->tc4_weights.p || !h->tc_weights.p) {          // first use of the handle: allocate and build everything once
+    int rc = tc4_prepare(h);
+    if (rc) return rc;
+    h->tc4_train_dirty = false;
+    return UBD_OK;
+  }
+  if (h->tc4_train_dirty) {
+    const int64_t* d_offs = reinterpret_cast<const int64_t*>((uint8_t*)h->tc_weights.p + kTcZeroOff + tc::ZERO_BYTES + 64);
+    tc4::build_img_tf32_kernel<<<UBD_NLAYERS_DIL, 256, 0, h->stream>>>(h->d_params, d_offs, d_offs + 6, (uint8_t*)h->tc4_weights.p);
+    ++h->launches;
+    UBD_CUDA(cudaGetLastError());
+    h->tc4_train_dirty = false;
+  }
+  return UBD_OK;
+}
+
 // layer 0..5 = conv2d_1..6; layer 6 = the stem's L2 as a dense conv with `in` = uint8 grey image and L1
 // computed by the producer warps (l1 != nullptr).
 static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer, int n, int hh, int ww, int d,
                               int out_mode, int out_pad = UBD_MAP_PAD, const tc::HeadArgs* head = nullptr,
-                              const tc::L1Args* l1 = nullptr) {
+                              const tc::L1Args* l1 = nullptr, const uint8_t* wb_override = nullptr, bool train = false) {
   if (h->precision == UBD_FP32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32, bf16 or f16");
-  int rc = tc4_prepare(h);
+  int rc = train ? tc4_prepare_train(h) : tc4_prepare(h);
   if (rc) return rc;
   const bool bf16 = ubd_is16(h);
   const uint8_t* base = (const uint8_t*)h->tc4_weights.p;
   const uint8_t* wb = bf16 ? base + kTc4Tf32 + (size_t)layer * tc4::WB_BYTES_BF16 : base + (size_t)layer * tc4::WB_BYTES_TF32;
+  if (wb_override) wb = wb_override;         // e.g. the flipped-kernel images of the backward-data pass
   const int sw = ww <= tc4::SW_MAX ? ww : tc4::SW_MAX;
   const int n_strips = (ww + sw - 1) / sw;
   const long long rows = (long long)n * n_strips * hh;

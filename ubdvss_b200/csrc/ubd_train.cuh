@@ -373,7 +373,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 head_bwd_data_kernel(const float* __restrict__ dlogits, const float4* __restrict__ a9, float4* __restrict__ g9,
-                     const float* __restrict__ hk, int n_out, int N, int H, int W, int mpad) {
+                     const float* __restrict__ hk, int n_out, int N, int H, int W, int mpad, int rnd) {
   __shared__ float s_k[UBD_NF * (1 + UBD_MAX_CLASSES)];
   for (int i = threadIdx.x; i < UBD_NF * n_out; i += blockDim.x) s_k[i] = hk[i];
   __syncthreads();
@@ -395,8 +395,13 @@ head_bwd_data_kernel(const float* __restrict__ dlogits, const float4* __restrict
   for (int pl = 0; pl < UBD_NG; ++pl) {
     const size_t idx = act_index(n, pl, y, x, H, W, mpad);
     const float4 a = __ldg(&a9[idx]);
-    g9[idx] = make_float4(a.x > 0.f ? g[4 * pl] : 0.f, a.y > 0.f ? g[4 * pl + 1] : 0.f,
-                          a.z > 0.f ? g[4 * pl + 2] : 0.f, a.w > 0.f ? g[4 * pl + 3] : 0.f);
+    float4 o = make_float4(a.x > 0.f ? g[4 * pl] : 0.f, a.y > 0.f ? g[4 * pl + 1] : 0.f,
+                           a.z > 0.f ? g[4 * pl + 2] : 0.f, a.w > 0.f ? g[4 * pl + 3] : 0.f);
+    if (rnd) {        // the tensor-core backward reads this map: round (magnitude, half up) to the tf32 grid instead of truncating
+      o.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u); o.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
+      o.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u); o.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
+    }
+    g9[idx] = o;
   }
 }
 

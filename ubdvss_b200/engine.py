@@ -221,6 +221,17 @@ class Engine:
         check(self._h, self._lib.ubd_debug_dilated_layer(self._h, ptr(x), ptr(out), layer, n, mh, mw, _lib.PRECISIONS[precision]))
         return out
 
+    def debug_wgrad(self, x_nhwc, g_nhwc, dilation: int):
+        """(dK (3,3,24,24), dB (24,)) of one dilated layer from its input map and output gradient (tcgen05 wgrad kernel)."""
+        x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
+        g = np.ascontiguousarray(g_nhwc, dtype=np.float32)
+        n, mh, mw, c = x.shape
+        assert c == 24 and g.shape == x.shape
+        dk = np.empty((3, 3, 24, 24), np.float32)
+        db = np.empty(24, np.float32)
+        check(self._h, self._lib.ubd_debug_wgrad(self._h, ptr(x), ptr(g), n, mh, mw, int(dilation), ptr(dk), ptr(db)))
+        return dk, db
+
     def set_stream(self, cuda_stream: int | None):
         check(self._h, self._lib.ubd_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
