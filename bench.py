@@ -180,6 +180,53 @@ def time_cpu(weights, images_u8, thr, n_classes, steps, warmup):
     return images_u8.shape[0] * steps / dt, dt / steps, cores
 
 
+def measure_traffic(args, precision):
+    """(DRAM bytes per launch of the dilated-conv kernel, DRAM bytes of the whole step, source) from an ncu pass over one
+    step of this very configuration, or (None, None, reason)."""
+    import csv
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, None, "ncu not found"
+    log = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
+    cmd = [ncu, "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "--cache-control", "none", "--csv", "--log-file", log, sys.executable, os.path.abspath(__file__), "--traffic-child",
+           "--config", args.config, "--precision", precision, "--no-train", "--no-cpu-baseline"]
+    if args.batch:
+        cmd += ["--batch", str(args.batch)]
+    if args.size:
+        cmd += ["--size", str(args.size)]
+    try:
+        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600, check=True)
+        per = {}
+        for r in csv.reader(open(log)):
+            if len(r) > 14 and r[0].isdigit() and r[12].startswith("dram__bytes"):
+                v = float(r[14].replace(",", ""))
+                unit = r[13].lower()
+                v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+                k = per.setdefault(int(r[0]), [r[4], 0.0])
+                k[1] += v
+        if not per:
+            return None, None, "ncu produced no kernel records"
+        step = sum(v for _, v in per.values())
+        import re
+        dil = []
+        for name, v in per.values():              # the dilated layers: dilconv_col_kernel<BF16, L1SRC = 0, PIPE>
+            mt = re.search(r"dilconv_col_kernel<\D*(\d)\D+(\d)", name)
+            if mt and mt.group(2) == "0":
+                dil.append(v)
+        per_launch = sum(dil) / len(dil) if dil else None
+        return per_launch, step, f"ncu pass in this run ({len(per)} kernel launches of one step, --cache-control none)"
+    except Exception as e:      # noqa: BLE001
+        return None, None, f"ncu pass failed: {type(e).__name__}"
+    finally:
+        try:
+            os.unlink(log)
+        except OSError:
+            pass
+
+
 _REAL_STDOUT = None
 
 
@@ -231,6 +278,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-E training-step measurement")
     ap.add_argument("--sync-api", action="store_true", help="time the synchronous ubd_segment[_dev] calls instead of submit/wait")
+    ap.add_argument("--no-extra", action="store_true", help="skip the f16 / bf16 container lines beside a tf32 run")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu pass that measures the DRAM bytes of one step")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -299,7 +349,18 @@ def main():
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
-    def run_dev(steps):
+    if args.traffic_child:
+        # profiled by the parent under ncu: two warm-up steps, then ONE step between cudaProfilerStart / Stop
+        for k in range(3):
+            if k == 2:
+                torch.cuda.synchronize()
+                torch.cuda.cudart().cudaProfilerStart()
+            eng.segment_dev(d_imgs[k & 1].data_ptr(), _lib.UBD_U8, B, H, W, thr, min_area_x2, _lib.PREPROC_MOBILENET, max_comps=cap)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return 0
+
+    def run_dev(steps, eng=eng):
         """`steps` batches through the device-resident entry points; returns the last batch's component counts."""
         counts = None
         if args.sync_api:
@@ -342,6 +403,25 @@ def main():
     ccl_ms, head_ms = eng.stat("ccl_ms"), eng.stat("head_ms")
     host_ms = [eng.stat(f"host_ms{i}") / args.steps for i in range(5)]
     eng.set_option("profile", 0)
+
+    # the same loop with 16-bit map containers, reported beside the headline (never instead of it): "f16" = IEEE-half maps and
+    # weights with fp32 accumulation - the 10-bit significand a tf32 MMA reads, at half the map traffic - and "bf16"
+    other = {}
+    if precision == "tf32" and not args.no_extra:
+        for p2 in ("f16", "bf16"):
+            e2 = Engine(device=local_rank, precision=p2, n_classes=n_classes)
+            e2.set_weights(weights)
+            e2.set_stream(stream.cuda_stream)
+            run_dev(args.warmup, e2)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            run_dev(args.steps, e2)
+            a1.record(stream)
+            barrier()
+            other[p2] = a0.elapsed_time(a1)
+            e2.set_stream(None)
+            del e2
 
     # end to end through the host-buffer C-ABI calls (what ModelRunner.predict / predict_stream do): pinned host
     # images in, mask + components out, every copy inside the timed region
@@ -387,9 +467,13 @@ def main():
         from ubdvss_b200 import losses as ulosses
         eng.set_stream(None)
         tb = 32
-        tx = np.concatenate([synth.synth_images(8, 512, 512, seed=40 + rank)] * (tb // 8))
-        ty = np.concatenate([synth.synth_targets(8, 128, 128, 0, seed=40 + rank)] * (tb // 8))
-        model = B200Model(NetConfig(), device=local_rank, weights=usynth.synth_weights(0, seed=1234, calibrated=True))
+        # pinned host batches (what a loader hands over); a tf32 handle runs the dilated layers' forward, dgrad and wgrad on
+        # the tensor cores (UBD_TRAIN_PRECISION=fp32: the exact FP32-pipe step)
+        train_prec = os.environ.get("UBD_TRAIN_PRECISION", "tf32")
+        tx = torch.from_numpy(np.concatenate([synth.synth_images(8, 512, 512, seed=40 + rank)] * (tb // 8))).pin_memory().numpy()
+        ty = torch.from_numpy(np.concatenate([synth.synth_targets(8, 128, 128, 0, seed=40 + rank)] * (tb // 8)).astype(np.int32)).pin_memory().numpy()
+        model = B200Model(NetConfig(), device=local_rank, precision=train_prec,
+                          weights=usynth.synth_weights(0, seed=1234, calibrated=True))
         model.compile(Adam(1e-3), loss=ulosses.get_loss(False))
         if dist is not None:
             model.set_distributed(True)
@@ -397,17 +481,18 @@ def main():
             model.train_on_batch(tx, ty, preprocessing="mobilenet_like")
         barrier()
         t0 = time.perf_counter()
-        tsteps = max(2, min(args.steps, 5))
+        tsteps = max(2, min(args.steps, 20))
         for _ in range(tsteps):
             out = model.train_on_batch(tx, ty, preprocessing="mobilenet_like")
         torch.cuda.synchronize()
         train_ms = (time.perf_counter() - t0) * 1e3 / tsteps
         train_loss = out[0]
 
-    t = torch.tensor([ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, train_ms, other.get("f16", 0.0), other.get("bf16", 0.0)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max, train_ms_max = float(t[0]), float(t[1]), float(t[2])
+    other = {k: float(t[3 + i]) for i, k in enumerate(("f16", "bf16")) if k in other}
     total_images = B * world * args.steps
     value = total_images / (ms_max / 1e3)
     e2e_value = total_images / (e2e_ms_max / 1e3)
@@ -425,16 +510,13 @@ def main():
         flops_per_launch = 2.0 * DIL_MAC_PER_MAP_PX * q_px * imgs_per_launch
         achieved_tf = flops_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
         stem_flops_per_step = 2.0 * (33 + 792 + 792 / 4.0) * (H // 2) * (W // 2) * B      # L1 + L2 at half, L3 at quarter resolution
-        traffic, traffic_src, wasted = None, None, None
-        try:    # DRAM bytes from the committed ncu captures of this round (profiles/traffic.json says which)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[precision]
-            scale = imgs_per_launch * (H * W / 1048576.0) / tj["images_per_launch"]
-            traffic = tj["dram_bytes_per_launch"] * scale
-            traffic_src = tj["source"]
-            if "dram_bytes_per_step" in tj:
-                wasted = tj["dram_bytes_per_step"] * (B * H * W / 1048576.0 / tj["images_per_step"]) / (ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0) * B)
-        except Exception:
-            pass
+        # DRAM bytes of one step, measured in this run: a child process runs one step under
+        # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none` (caches left as in a real run)
+        traffic, traffic_src, wasted, step_dram = None, None, None, None
+        if world == 1 and not args.no_traffic:
+            traffic, step_dram, traffic_src = measure_traffic(args, precision)
+            if step_dram:
+                wasted = step_dram / (ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0) * B)
         step_flops = 2.0 * ALGO_MAC_PER_INPUT_PX * H * W * B
         roof = {"bound": "tensor", "kernel": "tc4::dilconv_col_kernel: dilated 3x3 conv 24->24 (L4-L9), one layer of one chunk per launch",
                 "achieved": achieved_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved_tf / peak_burst if peak_burst else None,
@@ -452,7 +534,7 @@ def main():
                                "tensor_frac": step_flops * value / (B * world) / 1e12 / peak_burst if peak_burst else None,
                                "hbm_frac": ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0) * (value / world) / (pk["hbm_gbs"] * 1e9),
                                "algorithmic_bytes_per_image": ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0),
-                               "wasted_traffic_ratio": wasted},
+                               "dram_bytes_per_step": step_dram, "wasted_traffic_ratio": wasted},
                 "cc": {"ms_per_step": ccl_ms / args.steps, "algorithmic_bytes_per_step": 5 * q_px * B,
                        "hbm_frac": 5 * q_px * B / (ccl_ms / args.steps / 1e3) / (pk["hbm_gbs"] * 1e9) if ccl_ms else None},
                 "stage_ms_per_step": {"stem": stem_ms / args.steps, "dilated": dil_ms / args.steps,
@@ -467,8 +549,13 @@ def main():
                         "d2h_bytes_per_step": int(mask_h[0].nbytes + 4 * B + 44 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum()),
                 "components_per_image": float(counts.sum()) / B}
+        if other:
+            line["other_containers"] = {k: {"value": total_images / (v / 1e3), "unit": "images/sec", "ms_per_step": v / args.steps,
+                                            "note": {"f16": "IEEE-half maps + weights, fp32 accumulate: tf32's 10-bit significand, half the map bytes; saturates at 65504",
+                                                     "bf16": "bf16 maps + weights, fp32 accumulate (configs[3] precision)"}[k]}
+                                        for k, v in other.items()}
         if not args.no_train:
-            line["train_step"] = {"config": "configs[4]: forward + losses.py loss + backward + Adam, batch 32 of 512x512 per GPU, fp32"
+            line["train_step"] = {"config": f"configs[4]: forward + losses.py loss + backward + Adam, batch 32 of 512x512 per GPU, {train_prec}"
                                             + (", gradient all-reduce over NCCL inside libubd (ubd_allreduce_grads)" if world > 1 else ""),
                                   "ms_per_step": train_ms_max, "images_per_sec": 32 * world / (train_ms_max / 1e3),
                                   "loss": train_loss}
