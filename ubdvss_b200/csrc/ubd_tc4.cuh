@@ -110,13 +110,15 @@ constexpr int L1_THREADS = 32 * L1_WARPS;
 constexpr int THREADS_L1 = THREADS + L1_THREADS;
 constexpr int TMEM_COLS = 256;                            // per segment one tile of 4 groups x 32 columns
 
+constexpr int HEAD_STRIDE = 36;                           // 1 + UBD_MAX_CLASSES = 33 outputs, padded to whole float4s
 template <bool BF16> struct Smem {
   static constexpr int NS = BF16 ? NS_BF16 : NS_TF32;
   static constexpr int SLOT = BF16 ? SLOT_BYTES_BF16 : SLOT_BYTES_TF32;
   static constexpr int WB = BF16 ? WB_BYTES_BF16 : WB_BYTES_TF32;
   uint8_t slots[NS * SLOT];
   uint8_t wimg[WB];                                       // weight images, then bias[32]
-  float headw[UBD_NF * (1 + UBD_MAX_CLASSES) + 1 + UBD_MAX_CLASSES];
+  __align__(16) float headw[(UBD_NF + 1) * HEAD_STRIDE];   // head kernel [24][HEAD_STRIDE] (columns >= n_out zero), then the bias row
+  __align__(16) float hstage[BF16 ? 8 * 32 * (1 + UBD_MAX_CLASSES) : 4];   // class head: per epilogue warp 32 px x n_out logits (coalesced write-out)
   uint64_t full[NS], empty[NS], gfull[8], gempty[8], wbar;
   uint32_t tmem_base;
   int abort_flag;
@@ -207,7 +209,7 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
   const uint4* in = in_;
   uint4* out = out_;
   const uint8_t* wb = wb_;
-  int d = d_, out_mode = out_mode_;
+  int d = d_, out_mode = L1SRC ? 3 : out_mode_;            // the L1-producer variant only ever writes the parity-split map (dead epilogues compile out)
   if constexpr (PIPE) {
     layer = (int)blockIdx.x % UBD_NLAYERS_DIL;
     kidx = (int)blockIdx.x / UBD_NLAYERS_DIL;
@@ -270,8 +272,10 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
     for (int c = 0; c < UBD_NF; ++c) bias[c] = __ldg(reinterpret_cast<const float*>(wb + WBYTES) + c);
     if (out_mode == 2) {
       const int et = (int)threadIdx.x - 128;                 // 0..255 over the epilogue warps
-      for (int i = et; i < UBD_NF * head.n_out; i += 256) S.headw[i] = head.hk[i];
-      for (int i = et; i < head.n_out; i += 256) S.headw[UBD_NF * head.n_out + i] = head.hb[i];
+      for (int i = et; i < (UBD_NF + 1) * HEAD_STRIDE; i += 256) {
+        const int c = i / HEAD_STRIDE, oc = i % HEAD_STRIDE;
+        S.headw[i] = oc < head.n_out ? (c < UBD_NF ? head.hk[c * head.n_out + oc] : head.hb[oc]) : 0.f;
+      }
     }
   }
   tc_fence_before();
@@ -503,13 +507,50 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
           } else if (out_mode == 2) {
             const size_t p = ((size_t)pc.n * h + y) * w + x;
             const float* hw = S.headw;
-            float* lo = head.logits ? head.logits + p * head.n_out : nullptr;
-            for (int oc = 0; oc < head.n_out; ++oc) {
-              float acc = hw[UBD_NF * head.n_out + oc];
+            if (head.n_out == 1) {
+              float acc = hw[UBD_NF * HEAD_STRIDE];
 #pragma unroll
-              for (int c = 0; c < UBD_NF; ++c) acc = fmaf(a[c], hw[c * head.n_out + oc], acc);
-              if (lo) lo[oc] = acc;
-              if (oc == 0 && head.mask) head.mask[p] = acc > head.thr ? 1 : 0;
+              for (int c = 0; c < UBD_NF; ++c) acc = fmaf(a[c], hw[c * HEAD_STRIDE], acc);
+              if (head.logits) head.logits[p] = acc;
+              if (head.mask) head.mask[p] = acc > head.thr ? 1 : 0;
+            } else {
+              // class head (net.py:307-311, up to 33 outputs): weights as broadcast float4 loads, packed fp32x2 FMAs over
+              // pairs of outputs; groups of four outputs beyond n_out are skipped (warp-uniform)
+              const int n4 = (head.n_out + 3) >> 2;
+              float2 acc2[HEAD_STRIDE / 2];
+#pragma unroll
+              for (int g4 = 0; g4 < HEAD_STRIDE / 4; ++g4) {
+                if (g4 < n4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(hw + UBD_NF * HEAD_STRIDE + 4 * g4);
+                  acc2[2 * g4] = make_float2(b4.x, b4.y); acc2[2 * g4 + 1] = make_float2(b4.z, b4.w);
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < UBD_NF; ++c) {
+                const float2 aa = make_float2(a[c], a[c]);
+#pragma unroll
+                for (int g4 = 0; g4 < HEAD_STRIDE / 4; ++g4) {
+                  if (g4 < n4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(hw + c * HEAD_STRIDE + 4 * g4);
+                    acc2[2 * g4] = ffma2(aa, make_float2(w4.x, w4.y), acc2[2 * g4]);
+                    acc2[2 * g4 + 1] = ffma2(aa, make_float2(w4.z, w4.w), acc2[2 * g4 + 1]);
+                  }
+                }
+              }
+              if (head.mask) head.mask[p] = acc2[0].x > head.thr ? 1 : 0;
+              if (head.logits) {
+                float* lo = BF16 ? S.hstage + ((size_t)(warp - 4) * 32 + lane) * head.n_out : head.logits + p * head.n_out;
+#pragma unroll
+                for (int g4 = 0; g4 < HEAD_STRIDE / 4; ++g4) {
+                  if (g4 < n4) {
+                    const int oc = 4 * g4;
+                    lo[oc] = acc2[2 * g4].x;
+                    if (oc + 1 < head.n_out) lo[oc + 1] = acc2[2 * g4].y;
+                    if (oc + 2 < head.n_out) lo[oc + 2] = acc2[2 * g4 + 1].x;
+                    if (oc + 3 < head.n_out) lo[oc + 3] = acc2[2 * g4 + 1].y;
+                  }
+                }
+              }
             }
           } else if (out_mode == 3) {
             constexpr int NGO = BF16 ? 3 : UBD_NG;
@@ -549,6 +590,22 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
               }
               __stcs(o_px + (size_t)g * wpo, u);
             }
+          }
+        }
+        if constexpr (BF16) {
+          if (out_mode == 2 && head.n_out > 1 && head.logits) {
+            // the warp's 32 (or fewer, multiple of 4) consecutive pixels x n_out logits are contiguous in the NHWC output:
+            // write them as coalesced float4s instead of n_out strided 4-byte stores per pixel
+            __syncwarp();
+            const int xs0 = seg * SEG + quad * 32;
+            const int cnt = min(32, pc.nw - xs0);
+            if (cnt > 0) {
+              const float4* src4 = reinterpret_cast<const float4*>(S.hstage + (size_t)(warp - 4) * 32 * head.n_out);
+              float4* dst4 = reinterpret_cast<float4*>(head.logits + (((size_t)pc.n * h + y) * w + pc.x0 + xs0) * head.n_out);
+              const int n16 = cnt * head.n_out / 4;
+              for (int i = lane; i < n16; i += 32) dst4[i] = src4[i];
+            }
+            __syncwarp();
           }
         }
         if (warp == 4) { TC4_TRACE(2, 3); TC4_TRACE_NEXT(); }
