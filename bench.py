@@ -227,6 +227,26 @@ def measure_traffic(args, precision):
             pass
 
 
+def pin_to_gpu_cpus(index):
+    """Restrict this rank to the CPUs NVML reports as local to its GPU (pinned staging buffers are then first-touched on
+    that NUMA node).  Returns a short description for the JSON line; any failure leaves the affinity alone."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.replace(",", "").isdigit() else index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        want = cpus & cur
+        if want and want != cur:
+            os.sched_setaffinity(0, want)
+        return f"{len(want or cur)} of {len(cur)} CPUs (NVML affinity of GPU {phys})"
+    except Exception as e:      # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
+
+
 _REAL_STDOUT = None
 
 
@@ -329,6 +349,7 @@ def main():
     from ubdvss_b200 import _lib
     from ubdvss_b200.engine import Engine
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_cpus(local_rank)         # before any pinned allocation: first touch lands on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -547,7 +568,7 @@ def main():
                 "api": "ubd_segment_dev / ubd_segment" if args.sync_api else f"ubd_segment_submit[_dev] + ubd_segment_wait ({DEPTH} batches in flight)",
                 "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(imgs[0].nbytes),
                         "d2h_bytes_per_step": int(mask_h[0].nbytes + 4 * B + 44 * n_comp_last), "ms_per_step": e2e_ms_max / args.steps},
-                "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum()),
+                "cpu_affinity": numa, "gpu_launches": int(launches), "roofline": roof, "components_last_step": int(counts.sum()),
                 "components_per_image": float(counts.sum()) / B}
         if other:
             line["other_containers"] = {k: {"value": total_images / (v / 1e3), "unit": "images/sec", "ms_per_step": v / args.steps,

@@ -276,6 +276,7 @@ extern "C" int ubd_set_weights(ubd_handle h, const float* const* arrays, const i
   h->tc_weights_dirty = true;
   h->tc4_weights_dirty = true;
   h->tc4_train_dirty = true;
+  h->headw_dirty = true;
   h->stem_weights_dirty = true;
   return UBD_OK;
 }

@@ -88,6 +88,8 @@ struct ubd_handle_s {
   DevBuf tc_trace;                // optional event trace of CTA 0 (option "tc_trace")
   DevBuf tc_weights;              // per-layer UMMA B-operand images (+ bias)
   DevBuf tc4_weights;             // per-layer weight images of the column-rotating kernel (+ bias)
+  DevBuf headw_dev;               // padded head kernel + bias, staged into the constant bank before a head launch
+  bool headw_dirty = true;
   DevBuf tc4_bwd;                 // training: flipped kernels (HWIO) + zero bias + offsets, then their tf32 weight images
   bool bwd_offs_ready = false;
   int opt_train_tc_bits = 7;
@@ -107,7 +109,7 @@ struct ubd_handle_s {
   std::vector<DevBuf*> all_bufs() {
     std::vector<DevBuf*> v = {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,
             &cls_sums, &out_index, &row_ext, &run_label, &pipe_ring, &pipe_flags, &prep_tab, &prep_a, &prep_b, &prep_in, &prep_out,
-            &tc_weights, &tc4_weights, &tc4_bwd, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
+            &tc_weights, &tc4_weights, &tc4_bwd, &headw_dev, &tc_trace, &stem_wimg, &l2dense, &t_acts, &t_grads_act,
             &t_scratch, &t_partials, &d_grads, &d_adam_m, &d_adam_v, &d_ytrue, &d_dlogits, &t_loss, &d_metric};
     for (ResultSlot& R : rs)
       for (DevBuf* b : {&R.hdr, &R.out_recs, &R.hull_pts, &R.box_recs, &R.d_images, &R.d_mask, &R.d_logits}) v.push_back(b);

@@ -110,14 +110,44 @@ constexpr int L1_THREADS = 32 * L1_WARPS;
 constexpr int THREADS_L1 = THREADS + L1_THREADS;
 constexpr int TMEM_COLS = 256;                            // per segment one tile of 4 groups x 32 columns
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 constexpr int HEAD_STRIDE = 36;                           // 1 + UBD_MAX_CLASSES = 33 outputs, padded to whole float4s
+// Head kernel of the launch in the constant bank: [24][HEAD_STRIDE] (columns >= n_out zero), then the bias row.  Every
+// lane of a warp needs the same weight, and from shared memory a uniform 16-byte load still costs four LSU passes (the
+// class head was bound by them: ncu, 207 LDS.128 per warp and row); as constant operands the weights ride inside the FMAs.
+// One bank per device: the launcher copies the handle's padded head (3.6 KB, device to device) in front of every head
+// launch on its stream; two handles running class-head launches concurrently on one device are not supported.
+__constant__ float c_headw[(UBD_NF + 1) * HEAD_STRIDE];
+
+// Class head of one pixel: acc[4 g4 .. 4 g4 + 3] = bias + sum_c a[c] * hk[c][4 g4 ..] for N4 groups of four outputs.  N4 is a
+// template parameter so that the loops unroll into FMAs with immediate constant-bank operands.
+template <int N4>
+__device__ __forceinline__ void head_fma(const float (&a)[UBD_NF], float (&acc)[HEAD_STRIDE]) {
+#pragma unroll
+  for (int o = 0; o < 4 * N4; ++o) acc[o] = c_headw[UBD_NF * HEAD_STRIDE + o];
+#pragma unroll
+  for (int c = 0; c < UBD_NF; ++c)
+#pragma unroll
+    for (int o = 0; o < 4 * N4; ++o) acc[o] = fmaf(a[c], c_headw[c * HEAD_STRIDE + o], acc[o]);
+}
+
+__global__ void build_headw_kernel(const float* __restrict__ hk, const float* __restrict__ hb, int n_out, float* __restrict__ dst) {
+  for (int i = threadIdx.x; i < (UBD_NF + 1) * HEAD_STRIDE; i += blockDim.x) {
+    const int c = i / HEAD_STRIDE, oc = i % HEAD_STRIDE;
+    dst[i] = oc < n_out ? (c < UBD_NF ? hk[c * n_out + oc] : hb[oc]) : 0.f;
+  }
+}
+
 template <bool BF16> struct Smem {
   static constexpr int NS = BF16 ? NS_BF16 : NS_TF32;
   static constexpr int SLOT = BF16 ? SLOT_BYTES_BF16 : SLOT_BYTES_TF32;
   static constexpr int WB = BF16 ? WB_BYTES_BF16 : WB_BYTES_TF32;
   uint8_t slots[NS * SLOT];
   uint8_t wimg[WB];                                       // weight images, then bias[32]
-  __align__(16) float headw[(UBD_NF + 1) * HEAD_STRIDE];   // head kernel [24][HEAD_STRIDE] (columns >= n_out zero), then the bias row
   __align__(16) float hstage[BF16 ? 8 * 32 * (1 + UBD_MAX_CLASSES) : 4];   // class head: per epilogue warp 32 px x n_out logits (coalesced write-out)
   uint64_t full[NS], empty[NS], gfull[8], gempty[8], wbar;
   uint32_t tmem_base;
@@ -270,13 +300,6 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
   if (epi) {
 #pragma unroll
     for (int c = 0; c < UBD_NF; ++c) bias[c] = __ldg(reinterpret_cast<const float*>(wb + WBYTES) + c);
-    if (out_mode == 2) {
-      const int et = (int)threadIdx.x - 128;                 // 0..255 over the epilogue warps
-      for (int i = et; i < (UBD_NF + 1) * HEAD_STRIDE; i += 256) {
-        const int c = i / HEAD_STRIDE, oc = i % HEAD_STRIDE;
-        S.headw[i] = oc < head.n_out ? (c < UBD_NF ? head.hk[c * head.n_out + oc] : head.hb[oc]) : 0.f;
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -506,50 +529,35 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             }
           } else if (out_mode == 2) {
             const size_t p = ((size_t)pc.n * h + y) * w + x;
-            const float* hw = S.headw;
             if (head.n_out == 1) {
-              float acc = hw[UBD_NF * HEAD_STRIDE];
+              float acc = c_headw[UBD_NF * HEAD_STRIDE];
 #pragma unroll
-              for (int c = 0; c < UBD_NF; ++c) acc = fmaf(a[c], hw[c * HEAD_STRIDE], acc);
+              for (int c = 0; c < UBD_NF; ++c) acc = fmaf(a[c], c_headw[c * HEAD_STRIDE], acc);
               if (head.logits) head.logits[p] = acc;
               if (head.mask) head.mask[p] = acc > head.thr ? 1 : 0;
             } else {
-              // class head (net.py:307-311, up to 33 outputs): weights as broadcast float4 loads, packed fp32x2 FMAs over
-              // pairs of outputs; groups of four outputs beyond n_out are skipped (warp-uniform)
+              // class head (net.py:307-311, up to 33 outputs)
               const int n4 = (head.n_out + 3) >> 2;
-              float2 acc2[HEAD_STRIDE / 2];
+              float acc[HEAD_STRIDE];
 #pragma unroll
-              for (int g4 = 0; g4 < HEAD_STRIDE / 4; ++g4) {
-                if (g4 < n4) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(hw + UBD_NF * HEAD_STRIDE + 4 * g4);
-                  acc2[2 * g4] = make_float2(b4.x, b4.y); acc2[2 * g4 + 1] = make_float2(b4.z, b4.w);
-                }
+              for (int i = 0; i < HEAD_STRIDE; ++i) acc[i] = 0.f;
+              switch (n4) {
+                case 1: head_fma<1>(a, acc); break;
+                case 2: head_fma<2>(a, acc); break;
+                case 3: head_fma<3>(a, acc); break;
+                case 4: head_fma<4>(a, acc); break;
+                case 5: head_fma<5>(a, acc); break;
+                case 6: head_fma<6>(a, acc); break;
+                case 7: head_fma<7>(a, acc); break;
+                case 8: head_fma<8>(a, acc); break;
+                default: head_fma<9>(a, acc); break;
               }
-#pragma unroll
-              for (int c = 0; c < UBD_NF; ++c) {
-                const float2 aa = make_float2(a[c], a[c]);
-#pragma unroll
-                for (int g4 = 0; g4 < HEAD_STRIDE / 4; ++g4) {
-                  if (g4 < n4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(hw + c * HEAD_STRIDE + 4 * g4);
-                    acc2[2 * g4] = ffma2(aa, make_float2(w4.x, w4.y), acc2[2 * g4]);
-                    acc2[2 * g4 + 1] = ffma2(aa, make_float2(w4.z, w4.w), acc2[2 * g4 + 1]);
-                  }
-                }
-              }
-              if (head.mask) head.mask[p] = acc2[0].x > head.thr ? 1 : 0;
+              if (head.mask) head.mask[p] = acc[0] > head.thr ? 1 : 0;
               if (head.logits) {
                 float* lo = BF16 ? S.hstage + ((size_t)(warp - 4) * 32 + lane) * head.n_out : head.logits + p * head.n_out;
 #pragma unroll
-                for (int g4 = 0; g4 < HEAD_STRIDE / 4; ++g4) {
-                  if (g4 < n4) {
-                    const int oc = 4 * g4;
-                    lo[oc] = acc2[2 * g4].x;
-                    if (oc + 1 < head.n_out) lo[oc + 1] = acc2[2 * g4].y;
-                    if (oc + 2 < head.n_out) lo[oc + 2] = acc2[2 * g4 + 1].x;
-                    if (oc + 3 < head.n_out) lo[oc + 3] = acc2[2 * g4 + 1].y;
-                  }
-                }
+                for (int oc = 0; oc < HEAD_STRIDE; ++oc)
+                  if (oc < head.n_out) lo[oc] = acc[oc];
               }
             }
           } else if (out_mode == 3) {
@@ -851,6 +859,24 @@ static int tc4_prepare(ubd_handle h) {
   return UBD_OK;
 }
 
+// The head of an out_mode 2 launch goes into the constant bank (tc4::c_headw), stream-ordered in front of the launch.
+static int tc4_stage_head(ubd_handle h, const tc::HeadArgs* head) {
+  constexpr size_t kBytes = (size_t)(UBD_NF + 1) * tc4::HEAD_STRIDE * sizeof(float);
+  if (!h->headw_dev.p) {
+    UBD_CUDA(cudaMalloc(&h->headw_dev.p, kBytes));
+    h->headw_dev.cap = kBytes;
+    h->headw_dirty = true;
+  }
+  if (h->headw_dirty) {
+    tc4::build_headw_kernel<<<1, 256, 0, h->stream>>>(head->hk, head->hb, head->n_out, (float*)h->headw_dev.p);
+    ++h->launches;
+    UBD_CUDA(cudaGetLastError());
+    h->headw_dirty = false;
+  }
+  UBD_CUDA(cudaMemcpyToSymbolAsync(tc4::c_headw, h->headw_dev.p, kBytes, 0, cudaMemcpyDeviceToDevice, h->stream));
+  return UBD_OK;
+}
+
 // Training step: between two Adam updates only the six dilated tf32 images are needed (forward and, with flipped kernels,
 // backward-data launches).  Rebuild them alone and leave the full-rebuild flags set for the next inference call.
 static int tc4_prepare_train(ubd_handle h) {
@@ -888,6 +914,7 @@ static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer
   const int grid = (int)std::min<long long>(rows, h->n_sm);
   tc::HeadArgs ha{};
   if (head) ha = *head;
+  if (out_mode == 2 && head) { rc = tc4_stage_head(h, head); if (rc) return rc; }
   tc::L1Args la{};
   if (l1) la = *l1;
 #define UBD_TC4_LAUNCH(BF, L1S, THR)                                                                                   \
@@ -910,6 +937,7 @@ static int tc4_launch_pipeline(ubd_handle h, const void* in, int n, int hh, int 
   if (h->precision == UBD_FP32) UBD_FAIL(UBD_ERR_UNSUPPORTED, "tensor-core path needs tf32, bf16 or f16");
   int rc = tc4_prepare(h);
   if (rc) return rc;
+  if (head) { rc = tc4_stage_head(h, head); if (rc) return rc; }
   const bool bf16 = ubd_is16(h);
   const int ring = std::max(2, h->opt_pipe_ring);
   const size_t img_units = act_elems(1, hh, ww, UBD_MAP_PAD) / (bf16 ? 2 : 1);               // 16-byte units per map
