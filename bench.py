@@ -349,6 +349,7 @@ def main():
     from ubdvss_b200 import _lib
     from ubdvss_b200.engine import Engine
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
     numa = pin_to_gpu_cpus(local_rank)         # before any pinned allocation: first touch lands on the GPU's NUMA node
     dist = None
     if world > 1:
@@ -581,6 +582,7 @@ def main():
                                   "ms_per_step": train_ms_max, "images_per_sec": 32 * world / (train_ms_max / 1e3),
                                   "loss": train_loss}
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
             v, step_s, cores = time_cpu(weights, imgs[0][:args.cpu_sample], thr, n_classes, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
                                     "sample": f"3 steps x {args.cpu_sample} images of {H}x{W} (torch-CPU restatement + cv2)"}
