@@ -358,14 +358,19 @@ xty_kernel(XL xl, YL yl, PixelGeom g, int KY, float* __restrict__ partials /*[gr
   if ((int)threadIdx.x < KY) o[nout + threadIdx.x] = colsum;
 }
 
-// out[i] = sum_b partials[b][i] in block order (deterministic); two destinations (kernel, bias)
+// out[i] = sum_b partials[b][i] in a fixed order (deterministic); two destinations (kernel, bias).  Eight lanes share an
+// output: lane l adds the blocks b = l, l + 8, ... in order, then the eight sums are combined as a fixed tree.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nblocks, int stride,
                                        float* __restrict__ dst0, int n0, float* __restrict__ dst1, int n1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n0 + n1) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, l = t & 7;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * stride + i];
-  if (i < n0) dst0[i] = s; else dst1[i - n0] = s;
+  if (i < n0 + n1)
+    for (int b = l; b < nblocks; b += 8) s += partials[(size_t)b * stride + i];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (i < n0 + n1 && l == 0) { if (i < n0) dst0[i] = s; else dst1[i - n0] = s; }
 }
 
 // ------------------------------------------------------------------------------------------------
