@@ -674,9 +674,14 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
           return;
         }
         valid = 0u;
+        if (cm == 0u) {                                      // idle lane / column outside the map: nothing to load.  (Three
+#pragma unroll                                               // lanes of every warp are idle: without this exit each warp ran the
+          for (int q = 0; q < 9; ++q) r[q] = 0u;             // predicated edge path below on every row - ncu source page.)
+          return;
+        }
 #pragma unroll
         for (int ti = 0; ti < 3; ++ti) {
-          const bool rv = cm != 0u && iy0 + ti >= 0 && iy0 + ti < l1.H;
+          const bool rv = iy0 + ti >= 0 && iy0 + ti < l1.H;
 #pragma unroll
           for (int tj = 0; tj < 3; ++tj) {
             r[ti * 3 + tj] = 0u;
