@@ -122,6 +122,10 @@ constexpr int HEAD_STRIDE = 36;                           // 1 + UBD_MAX_CLASSES
 // One bank per device: the launcher copies the handle's padded head (3.6 KB, device to device) in front of every head
 // launch on its stream; two handles running class-head launches concurrently on one device are not supported.
 __constant__ float c_headw[(UBD_NF + 1) * HEAD_STRIDE];
+// L1 (separable 1 -> 24, grey input) of the stem launch: pw1[24] then b1[24].  Uniform across a warp, so they ride in the
+// FMAs as constant operands instead of twelve 16-byte shared-memory loads per pixel and row (the stem kernel keeps the
+// shared-memory pipe ~2/3 busy with MMA operand reads, table look-ups and the staging stores: ncu mio_throttle).
+__constant__ float c_l1w[2 * UBD_NF];
 
 // Class head of one pixel: acc[4 g4 .. 4 g4 + 3] = bias + sum_c a[c] * hk[c][4 g4 ..] for N4 groups of four outputs.  N4 is a
 // template parameter so that the loops unroll into FMAs with immediate constant-bank operands.
@@ -720,17 +724,9 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
                 if (valid & (1u << q)) a = fmaf(S.lut[b[q]], dwr[q], a);
             }
             // pointwise 1 -> 24, bias, ReLU: packed fp32x2 FMAs on 16-byte weight loads (pw1 at l1w[12..36), b1 at l1w[36..60))
-            const float2 aa = make_float2(a, a);
-            const float4* pw4 = reinterpret_cast<const float4*>(S.l1w + 12);
-            const float4* b4 = reinterpret_cast<const float4*>(S.l1w + 12 + UBD_NF);
             float o[UBD_NF];
 #pragma unroll
-            for (int g = 0; g < UBD_NG; ++g) {
-              const float4 pw = pw4[g], bb = b4[g];
-              const float2 lo = ffma2(aa, make_float2(pw.x, pw.y), make_float2(bb.x, bb.y));
-              const float2 hi = ffma2(aa, make_float2(pw.z, pw.w), make_float2(bb.z, bb.w));
-              o[4 * g] = fmaxf(lo.x, 0.f); o[4 * g + 1] = fmaxf(lo.y, 0.f); o[4 * g + 2] = fmaxf(hi.x, 0.f); o[4 * g + 3] = fmaxf(hi.y, 0.f);
-            }
+            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(fmaf(a, c_l1w[c], c_l1w[UBD_NF + c]), 0.f);
             if constexpr (BF16) {
 #pragma unroll
               for (int g = 0; g < 3; ++g)
@@ -920,6 +916,10 @@ static int tc4_launch_dilconv(ubd_handle h, const void* in, void* out, int layer
   tc::HeadArgs ha{};
   if (head) ha = *head;
   if (out_mode == 2 && head) { rc = tc4_stage_head(h, head); if (rc) return rc; }
+  if (l1) {       // pw1 and b1 into the constant bank (device-to-device, stream-ordered in front of the launch)
+    UBD_CUDA(cudaMemcpyToSymbolAsync(tc4::c_l1w, l1->pw1, UBD_NF * sizeof(float), 0, cudaMemcpyDeviceToDevice, h->stream));
+    UBD_CUDA(cudaMemcpyToSymbolAsync(tc4::c_l1w, l1->b1, UBD_NF * sizeof(float), UBD_NF * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  }
   tc::L1Args la{};
   if (l1) la = *l1;
 #define UBD_TC4_LAUNCH(BF, L1S, THR)                                                                                   \
