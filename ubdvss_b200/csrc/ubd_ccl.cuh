@@ -570,6 +570,10 @@ __device__ __forceinline__ long long ccl_cross(int ox, int oy, int ax, int ay, i
   return (long long)(ax - ox) * (by - oy) - (long long)(ay - oy) * (bx - ox);
 }
 
+// cv2.boxPoints(cv2.minAreaRect(contour)) of one kept component per warp: row extents -> integer strict hull ->
+// float32 rotating calipers in the operation order and with the tie rule of OpenCV's rotatingCalipers()
+// (modules/imgproc/src/rotcalipers.cpp, Copyright (C) 2000 Intel Corporation / OpenCV contributors, Apache-2.0 since
+// OpenCV 4.5; see the note in ubd_rect.cpp), so that the boxes are bit-identical to the host path and to cv2.
 __global__ void __launch_bounds__(32)
 ccl_boxes_kernel(const int* __restrict__ ext, const OutRec* __restrict__ recs, const CclTotals* __restrict__ totals,
                  BoxRec* __restrict__ boxes, int h, int w, int max_out) {

@@ -8,6 +8,12 @@
 // terms, ending at the contour's first point (top-most, then left-most pixel).  Against
 // cv2 4.13 on 5,795 contours the rounded x4 boxes agree as corner sets in 99.9 % of cases; the
 // rest are exact equal-area ties (documented in DESIGN.md, compared as ties in the tests).
+//
+// Attribution: rotating_calipers() below follows the structure, float32 operation order and tie rule of
+// rotatingCalipers() in OpenCV's modules/imgproc/src/rotcalipers.cpp (Copyright (C) 2000, Intel Corporation;
+// Copyright (C) OpenCV contributors; OpenCV 4.5+ is distributed under the Apache License, Version 2.0,
+// http://www.apache.org/licenses/LICENSE-2.0 - earlier releases under the 3-clause BSD license), because the boxes must
+// be bit-identical to cv2.minAreaRect's.  ccl_boxes_kernel in ubd_ccl.cuh is the same procedure, one warp per component.
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
