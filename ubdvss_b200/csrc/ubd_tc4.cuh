@@ -156,7 +156,7 @@ template <bool BF16> struct Smem {
   uint64_t full[NS], empty[NS], gfull[8], gempty[8], wbar;
   uint32_t tmem_base;
   int abort_flag;
-  float lut[256];                // L1-producer variant: uint8 -> preprocessed float
+  float lut[260];                // L1-producer variant: uint8 -> preprocessed float; entry 256 = 0 (a tap outside the image)
   __align__(16) float l1w[12 + UBD_NF + UBD_NF]; // dw1[9] (+3 pad), pw1[24], b1[24] (grey input)
 };
 
@@ -642,7 +642,7 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
     const int tl = (int)threadIdx.x - THREADS;              // 0 .. L1_THREADS-1 (table loads)
     const int t = (warp - 12) * L1_PXW + lane;              // staged pixel of this thread
     const uint8_t* img = reinterpret_cast<const uint8_t*>(in);
-    for (int i = tl; i < 256; i += L1_THREADS) S.lut[i] = l1.lut ? l1.lut[i] : (float)i;
+    for (int i = tl; i < 260; i += L1_THREADS) S.lut[i] = i < 256 ? (l1.lut ? l1.lut[i] : (float)i) : 0.f;
     for (int i = tl; i < 12 + 2 * UBD_NF; i += L1_THREADS)
       S.l1w[i] = i < 9 ? l1.dw1[i] : (i < 12 ? 0.f : (i < 12 + UBD_NF ? l1.pw1[i - 12] : l1.b1[i - 12 - UBD_NF]));
     asm volatile("bar.sync 1, %0;" ::"n"(L1_THREADS) : "memory");   // the L1 warps only
@@ -656,58 +656,61 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
       const int x = pc.x0 - 1 + t;                           // this thread's map column
       const bool use = lane < L1_PXW && t < pc.nw + 2;
       const bool okx = use && x >= 0 && x < w;
-      // image columns 2x - pad_l + {0,1,2}: validity mask and pointer of the first one
+      // image columns 2x - pad_l + {0,1,2}: validity mask and CLAMPED column offsets.  Every lane executes the same nine
+      // loads (a tap outside the image reads a clamped address and is replaced by table index 256, whose entry is 0), so
+      // the warps that own an image edge or idle lanes no longer serialise an edge path next to the interior one - the
+      // in-kernel trace showed the first warp of a strip 4 rows behind the others, pacing the whole ring.
       uint32_t cm = 0u;
+      int coff[3];
 #pragma unroll
       for (int tj = 0; tj < 3; ++tj) {
         const int ix = 2 * x - l1.pad_l + tj;
         if (okx && ix >= 0 && ix < l1.W) cm |= 1u << tj;
+        coff[tj] = min(max(ix, 0), l1.W - 1);
       }
-      const uint8_t* pcol = img + ((size_t)pc.n * l1.H) * l1.W + (2 * x - l1.pad_l);
+      const uint8_t* pimg = img + ((size_t)pc.n * l1.H) * l1.W;
       const size_t W1 = (size_t)l1.W;
-      // the 9 image bytes of map pixel (yy, x), one register each (0 where the tap is outside the image):
-      // nothing consumes them before the next row's arithmetic, so the loads really stay in flight
-      auto load9 = [&](int yy, uint32_t& valid, uint32_t (&r)[9]) {
+      // the 9 table indices of map pixel (yy, x), one register each: nothing consumes them before the next row's
+      // arithmetic, so the loads really stay in flight
+      auto load9 = [&](int yy, uint32_t (&r)[9]) {
         const int iy0 = 2 * yy - l1.pad_t;
-        const uint8_t* p = pcol + (ptrdiff_t)iy0 * (ptrdiff_t)W1;
-        if (cm == 7u && iy0 >= 0 && iy0 + 2 < l1.H) {        // interior patch: nine plain loads
-          r[0] = __ldg(p); r[1] = __ldg(p + 1); r[2] = __ldg(p + 2);
-          r[3] = __ldg(p + W1); r[4] = __ldg(p + W1 + 1); r[5] = __ldg(p + W1 + 2);
-          r[6] = __ldg(p + 2 * W1); r[7] = __ldg(p + 2 * W1 + 1); r[8] = __ldg(p + 2 * W1 + 2);
-          valid = 0x1FFu;
-          return;
-        }
-        valid = 0u;
-        if (cm == 0u) {                                      // idle lane / column outside the map: nothing to load.  (Three
-#pragma unroll                                               // lanes of every warp are idle: without this exit each warp ran the
-          for (int q = 0; q < 9; ++q) r[q] = 0u;             // predicated edge path below on every row - ncu source page.)
-          return;
-        }
+        if (iy0 >= 0 && iy0 + 2 < l1.H) {                    // (warp-uniform) all three image rows exist
+          const uint8_t* p = pimg + (size_t)iy0 * W1;
 #pragma unroll
-        for (int ti = 0; ti < 3; ++ti) {
-          const bool rv = iy0 + ti >= 0 && iy0 + ti < l1.H;
+          for (int ti = 0; ti < 3; ++ti)
 #pragma unroll
-          for (int tj = 0; tj < 3; ++tj) {
-            r[ti * 3 + tj] = 0u;
-            if (rv && (cm & (1u << tj))) r[ti * 3 + tj] = __ldg(p + ti * W1 + tj);
+            for (int tj = 0; tj < 3; ++tj) {
+              const uint32_t v = __ldg(p + ti * W1 + coff[tj]);
+              r[ti * 3 + tj] = (cm & (1u << tj)) ? v : 256u;
+            }
+        } else {
+#pragma unroll
+          for (int ti = 0; ti < 3; ++ti) {
+            const int iy = iy0 + ti;
+            const bool rv = iy >= 0 && iy < l1.H;
+            const uint8_t* p = pimg + (size_t)min(max(iy, 0), l1.H - 1) * W1;
+#pragma unroll
+            for (int tj = 0; tj < 3; ++tj) {
+              const uint32_t v = __ldg(p + coff[tj]);
+              r[ti * 3 + tj] = (rv && (cm & (1u << tj))) ? v : 256u;
+            }
           }
-          if (rv) valid |= cm << (3 * ti);
         }
       };
       int i = pc.j0 == 0 ? 1 : 0;                             // input rows that exist: jj = j0 - 1 + i in [0, R)
       const int i_end = min(pc.rows + 1, pc.R - pc.j0);
-      uint32_t valid = 0u, b[9];
+      uint32_t b[9];
 #pragma unroll
-      for (int q = 0; q < 9; ++q) b[q] = 0u;
-      if (i <= i_end) load9(pc.c + (pc.j0 - 1 + i) * d, valid, b);
+      for (int q = 0; q < 9; ++q) b[q] = 256u;
+      if (i <= i_end) load9(pc.c + (pc.j0 - 1 + i) * d, b);
       for (; i <= i_end && ok; ++i, ++lseq) {
         const uint32_t slot = ring_slot, ring_par = ring_phase ^ 1u;
         if (++ring_slot == NS) { ring_slot = 0; ring_phase ^= 1u; }
         if (warp == 12) TC4_TRACE(3, 0);
-        uint32_t nvalid = 0u, nb[9];
+        uint32_t nb[9];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) nb[q] = 0u;
-        if (i + 1 <= i_end) load9(pc.c + (pc.j0 + i) * d, nvalid, nb);
+        for (int q = 0; q < 9; ++q) nb[q] = 256u;
+        if (i + 1 <= i_end) load9(pc.c + (pc.j0 + i) * d, nb);
         ok = mbar_wait3(smem_u32(&S.empty[slot]), ring_par, abort_flag, gerr, 26, lseq);
         if (warp == 12) TC4_TRACE(3, 1);
         if (ok && use) {
@@ -715,14 +718,8 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
           if (okx) {
             // depthwise 3x3 (stride 2) on the preprocessed bytes, pointwise 1 -> 24, bias, ReLU
             float a = 0.f;
-            if (valid == 0x1FFu) {
 #pragma unroll
-              for (int q = 0; q < 9; ++q) a = fmaf(S.lut[b[q]], dwr[q], a);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 9; ++q)
-                if (valid & (1u << q)) a = fmaf(S.lut[b[q]], dwr[q], a);
-            }
+            for (int q = 0; q < 9; ++q) a = fmaf(S.lut[b[q]], dwr[q], a);
             // pointwise 1 -> 24, bias, ReLU: packed fp32x2 FMAs on 16-byte weight loads (pw1 at l1w[12..36), b1 at l1w[36..60))
             float o[UBD_NF];
 #pragma unroll
@@ -750,7 +747,6 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
         __syncwarp();
         if (ok && lane == 0) mbar_arrive(smem_u32(&S.full[slot]));
         if (warp == 12) { TC4_TRACE(3, 3); TC4_TRACE_NEXT(); }
-        valid = nvalid;
 #pragma unroll
         for (int q = 0; q < 9; ++q) b[q] = nb[q];
       }
