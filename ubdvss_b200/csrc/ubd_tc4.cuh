@@ -69,6 +69,10 @@ __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volati
 // (tests/test_gpu_tc.py::test_tf32_operands_are_truncated), so adding half a tf32 ulp is the whole rounding -
 // one integer instruction where cvt.rna.tf32.f32 is emulated with four on sm_100a.
 __device__ __forceinline__ float rna_mma(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
+// ReLU and that rounding in ONE instruction (VIADDMNMX): max(bits + half ulp, 0) as signed integers - a negative float is a
+// negative integer and becomes +0.0, a positive one gets its half ulp.  One issue slot instead of FMNMX + IADD for every
+// channel of every pixel in the L1 producers and the epilogues (the busiest scheduler of the stem kernel paces its ring).
+__device__ __forceinline__ uint32_t relu_rna_bits(float pre) { return (uint32_t)__viaddmax_s32(__float_as_int(pre), 0x1000, 0); }
 
 // One non-blocking probe of a barrier phase (the fast path of the waits on the MMA warps' critical path).
 __device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
@@ -515,7 +519,7 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
           const int x = pc.x0 + xs;
           float a[UBD_NF];
 #pragma unroll
-          for (int c = 0; c < UBD_NF; ++c) a[c] = out_mode == 4 ? __uint_as_float(v[c]) : fmaxf(__uint_as_float(v[c]) + bias[c], 0.f);
+          for (int c = 0; c < UBD_NF; ++c) a[c] = out_mode == 4 ? __uint_as_float(v[c]) : __uint_as_float(v[c]) + bias[c];     // pre-activation
           if (out_mode == 4) {
             // backward-data pass (training): the conv ran with the flipped kernel; gate by the ReLU of the layer below
             // (its saved activation, same layout as the output) and leave the gradient on the tf32 grid for the next MMAs
@@ -532,6 +536,8 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
               }
             }
           } else if (out_mode == 2) {
+#pragma unroll
+            for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(a[c], 0.f);
             const size_t p = ((size_t)pc.n * h + y) * w + x;
             if (head.n_out == 1) {
               float acc = c_headw[UBD_NF * HEAD_STRIDE];
@@ -570,19 +576,21 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             uint4* o_px = out + ((((size_t)pc.n * h + y) * 2 + (x & 1)) * NGO) * wps + PAD + (x >> 1);
             if constexpr (BF16) {
 #pragma unroll
+              for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(a[c], 0.f);
+#pragma unroll
               for (int g = 0; g < 3; ++g)
                 o_px[(size_t)g * wps] = make_uint4(pack16(a[8 * g], a[8 * g + 1], f16), pack16(a[8 * g + 2], a[8 * g + 3], f16),
                                                    pack16(a[8 * g + 4], a[8 * g + 5], f16), pack16(a[8 * g + 6], a[8 * g + 7], f16));
             } else {
 #pragma unroll
-              for (int g = 0; g < UBD_NG; ++g) {
-                float4 q = make_float4(rna_mma(a[4 * g]), rna_mma(a[4 * g + 1]), rna_mma(a[4 * g + 2]), rna_mma(a[4 * g + 3]));
-                o_px[(size_t)g * wps] = *reinterpret_cast<uint4*>(&q);
-              }
+              for (int g = 0; g < UBD_NG; ++g)
+                o_px[(size_t)g * wps] = make_uint4(relu_rna_bits(a[4 * g]), relu_rna_bits(a[4 * g + 1]), relu_rna_bits(a[4 * g + 2]), relu_rna_bits(a[4 * g + 3]));
             }
           } else if (BF16 && out_mode == 0) {
             // (streaming stores: the next layer reads this map after the whole sweep, long after L2 has turned over)
             uint4* o_px = out + (((size_t)out_n * h + y) * 3) * wpo + out_pad + x;
+#pragma unroll
+            for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(a[c], 0.f);
 #pragma unroll
             for (int g = 0; g < 3; ++g)
               __stcs(o_px + (size_t)g * wpo, make_uint4(pack16(a[8 * g], a[8 * g + 1], f16), pack16(a[8 * g + 2], a[8 * g + 3], f16),
@@ -592,9 +600,10 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             const bool rnd = !BF16 && (out_mode == 0 || out_mode == 5);
 #pragma unroll
             for (int g = 0; g < UBD_NG; ++g) {
-              float4 q = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
-              if (rnd) { q.x = rna_mma(q.x); q.y = rna_mma(q.y); q.z = rna_mma(q.z); q.w = rna_mma(q.w); }
-              uint4 u = *reinterpret_cast<uint4*>(&q);
+              uint4 u;
+              if (rnd) u = make_uint4(relu_rna_bits(a[4 * g]), relu_rna_bits(a[4 * g + 1]), relu_rna_bits(a[4 * g + 2]), relu_rna_bits(a[4 * g + 3]));
+              else u = make_uint4(__float_as_uint(fmaxf(a[4 * g], 0.f)), __float_as_uint(fmaxf(a[4 * g + 1], 0.f)),
+                                  __float_as_uint(fmaxf(a[4 * g + 2], 0.f)), __float_as_uint(fmaxf(a[4 * g + 3], 0.f)));
               if (out_mode == 5) {
                 // training forward: the map is also read by FP32 code (ReLU gates test a > 0, the head, the weight gradient),
                 // so the low bits are really cleared - a clamped 0 must stay 0, not half a tf32 ulp
@@ -721,10 +730,12 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
 #pragma unroll
             for (int q = 0; q < 9; ++q) a = fmaf(S.lut[b[q]], dwr[q], a);
             // pointwise 1 -> 24, bias, ReLU: packed fp32x2 FMAs on 16-byte weight loads (pw1 at l1w[12..36), b1 at l1w[36..60))
-            float o[UBD_NF];
+            float o[UBD_NF];                                   // pre-activation
 #pragma unroll
-            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(fmaf(a, c_l1w[c], c_l1w[UBD_NF + c]), 0.f);
+            for (int c = 0; c < UBD_NF; ++c) o[c] = fmaf(a, c_l1w[c], c_l1w[UBD_NF + c]);
             if constexpr (BF16) {
+#pragma unroll
+              for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(o[c], 0.f);
 #pragma unroll
               for (int g = 0; g < 3; ++g)
                 *reinterpret_cast<uint4*>(px + g * plane_bytes) =
@@ -733,8 +744,8 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             } else {
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g)
-                *reinterpret_cast<float4*>(px + g * plane_bytes) =
-                    make_float4(rna_mma(o[4 * g]), rna_mma(o[4 * g + 1]), rna_mma(o[4 * g + 2]), rna_mma(o[4 * g + 3]));
+                *reinterpret_cast<uint4*>(px + g * plane_bytes) =
+                    make_uint4(relu_rna_bits(o[4 * g]), relu_rna_bits(o[4 * g + 1]), relu_rna_bits(o[4 * g + 2]), relu_rna_bits(o[4 * g + 3]));
             }
           } else {
             // column outside the map: L2's zero padding
