@@ -193,6 +193,13 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+// ReLU inside the conversion (cvt ... .relu): the 16-bit epilogues and L1 producers spend no FMNMX on it
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, bool f16) {
+  uint32_t r;
+  if (f16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 constexpr int F16_FLAG_SLOT = 31;
 
 // in/out: padded row-interleaved maps (pad = PAD) of n_imgs images, in 16-byte units: tf32 maps have

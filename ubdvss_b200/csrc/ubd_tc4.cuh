@@ -39,7 +39,7 @@ namespace tc4 {
 
 using tc::smem_u32; using tc::elect_one; using tc::mbar_init; using tc::mbar_arrive; using tc::mbar_expect_tx;
 using tc::mbar_wait; using tc::bulk_g2s; using tc::umma_commit; using tc::tc_fence_before; using tc::tc_fence_after;
-using tc::make_desc; using tc::round_tf32; using tc::pack_bf16x2; using tc::pack16; using tc::HeadArgs;
+using tc::make_desc; using tc::round_tf32; using tc::pack_bf16x2; using tc::pack16; using tc::pack16_relu; using tc::HeadArgs;
 
 // Bounded wait like tc::mbar_wait; on a stall every warp leaves (code << 24 | info) in gerr[1 + warp].
 __device__ __forceinline__ bool mbar_wait3(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code, uint32_t info) {
@@ -576,11 +576,9 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             uint4* o_px = out + ((((size_t)pc.n * h + y) * 2 + (x & 1)) * NGO) * wps + PAD + (x >> 1);
             if constexpr (BF16) {
 #pragma unroll
-              for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(a[c], 0.f);
-#pragma unroll
               for (int g = 0; g < 3; ++g)
-                o_px[(size_t)g * wps] = make_uint4(pack16(a[8 * g], a[8 * g + 1], f16), pack16(a[8 * g + 2], a[8 * g + 3], f16),
-                                                   pack16(a[8 * g + 4], a[8 * g + 5], f16), pack16(a[8 * g + 6], a[8 * g + 7], f16));
+                o_px[(size_t)g * wps] = make_uint4(pack16_relu(a[8 * g], a[8 * g + 1], f16), pack16_relu(a[8 * g + 2], a[8 * g + 3], f16),
+                                                   pack16_relu(a[8 * g + 4], a[8 * g + 5], f16), pack16_relu(a[8 * g + 6], a[8 * g + 7], f16));
             } else {
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g)
@@ -590,11 +588,9 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             // (streaming stores: the next layer reads this map after the whole sweep, long after L2 has turned over)
             uint4* o_px = out + (((size_t)out_n * h + y) * 3) * wpo + out_pad + x;
 #pragma unroll
-            for (int c = 0; c < UBD_NF; ++c) a[c] = fmaxf(a[c], 0.f);
-#pragma unroll
             for (int g = 0; g < 3; ++g)
-              __stcs(o_px + (size_t)g * wpo, make_uint4(pack16(a[8 * g], a[8 * g + 1], f16), pack16(a[8 * g + 2], a[8 * g + 3], f16),
-                                                        pack16(a[8 * g + 4], a[8 * g + 5], f16), pack16(a[8 * g + 6], a[8 * g + 7], f16)));
+              __stcs(o_px + (size_t)g * wpo, make_uint4(pack16_relu(a[8 * g], a[8 * g + 1], f16), pack16_relu(a[8 * g + 2], a[8 * g + 3], f16),
+                                                        pack16_relu(a[8 * g + 4], a[8 * g + 5], f16), pack16_relu(a[8 * g + 6], a[8 * g + 7], f16)));
           } else {
             uint4* o_px = out + (((size_t)out_n * h + y) * UBD_NG) * wpo + out_pad + x;
             const bool rnd = !BF16 && (out_mode == 0 || out_mode == 5);
@@ -735,12 +731,10 @@ dilconv_col_kernel(const uint4* __restrict__ in_, uint4* __restrict__ out_, cons
             for (int c = 0; c < UBD_NF; ++c) o[c] = fmaf(a, c_l1w[c], c_l1w[UBD_NF + c]);
             if constexpr (BF16) {
 #pragma unroll
-              for (int c = 0; c < UBD_NF; ++c) o[c] = fmaxf(o[c], 0.f);
-#pragma unroll
               for (int g = 0; g < 3; ++g)
                 *reinterpret_cast<uint4*>(px + g * plane_bytes) =
-                    make_uint4(pack16(o[8 * g], o[8 * g + 1], f16), pack16(o[8 * g + 2], o[8 * g + 3], f16),
-                               pack16(o[8 * g + 4], o[8 * g + 5], f16), pack16(o[8 * g + 6], o[8 * g + 7], f16));
+                    make_uint4(pack16_relu(o[8 * g], o[8 * g + 1], f16), pack16_relu(o[8 * g + 2], o[8 * g + 3], f16),
+                               pack16_relu(o[8 * g + 4], o[8 * g + 5], f16), pack16_relu(o[8 * g + 6], o[8 * g + 7], f16));
             } else {
 #pragma unroll
               for (int g = 0; g < UBD_NG; ++g)
