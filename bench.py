@@ -555,7 +555,9 @@ def main():
                 "stem": {"kernels": "tc4::dilconv_col_kernel<L1SRC> (L1+L2) + tc::dilconv_tc_kernel (L3)" if stem_n >= 2 * max(dil_n, 1) / 6 - 0.5
                                     else "stemf::stem_fused_kernel (L1+L2+L3)",
                          "ms_per_step": stem_ms / args.steps, "share_of_step": stem_ms / ms if ms else None,
-                         "algorithmic_tflops": stem_flops_per_step / (stem_ms / args.steps / 1e3) / 1e12 if stem_ms else None},
+                         "algorithmic_tflops": stem_flops_per_step / (stem_ms / args.steps / 1e3) / 1e12 if stem_ms else None,
+                         "frac": stem_flops_per_step / (stem_ms / args.steps / 1e3) / 1e12 / peak_burst if stem_ms and peak_burst else None,
+                         "note": "two kernels (L1+L2, L3); as ONE kernel function the dilated layer above has the largest total time per step"},
                 "whole_step": {"algorithmic_tflops": step_flops * value / (B * world) / 1e12,
                                "tensor_frac": step_flops * value / (B * world) / 1e12 / peak_burst if peak_burst else None,
                                "hbm_frac": ALGO_BYTES_PER_IMAGE_1024 * (H * W / 1048576.0) * (value / world) / (pk["hbm_gbs"] * 1e9),
