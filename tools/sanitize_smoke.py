@@ -23,7 +23,15 @@ xf = (x.astype(np.float32) - 127.5) / 127.5
 eng.forward(xf, _lib.PREPROC_NONE)
 m = synth.stress_masks(3, 40, 72, seed=2)
 eng.postprocess(m, None, 10, want_labels=True)
-if prec == "fp32":
+if prec in ("fp32", "tf32"):     # tf32: tcgen05 forward / backward-data + the mma.sync weight-gradient kernels
     y = synth.synth_targets(2, 16, 80, 2, seed=1)
     p = eng.train_step(x, y, _lib.PREPROC_MOBILENET); eng.adam_step()
     print("train ok", p.tolist())
+    y3 = synth.synth_targets(3, 80, 256, 2, seed=2)       # several rows per CTA, two strips per half-resolution row
+    p = eng.train_step(x2, y3, _lib.PREPROC_MOBILENET)
+    print("train (large) ok", p.tolist())
+# pipelined calls: three batches in flight, CC on its own stream
+ts = [eng.segment_submit(x, thr, 10, _lib.PREPROC_MOBILENET) for _ in range(3)]
+for t in ts:
+    eng.segment_wait(t)
+print(prec, "pipelined ok")
