@@ -221,6 +221,22 @@ def test_wgrad_tcgen05_matches_numpy(d, shape):
     assert np.array_equal(dk, dk2) and np.array_equal(db, db2)          # fixed summation order
 
 
+def test_tensor_core_training_step_rgb_tf_padding():
+    """The tf32 step with a 3-channel input and TF 'same' stride-2 padding (fml_compatible = False): the stem variants the
+    grey / FML default does not exercise."""
+    w = onet.init_weights(3, seed=5, grey=False)
+    x = synth.synth_images(2, 64, 128, seed=6, channels=3)
+    y = synth.synth_targets(2, 16, 32, 3, seed=6)
+    xf = onet.preprocess(x.astype(np.float64), "mobilenet_like").astype(np.float32)
+    loss, _, ref_grads, _ = L.train_step_torch(w, xf, y, True, fml_compatible=False)
+    eng = _engine(grey=False, fml_compatible=False, n_classes=3, precision="tf32")
+    eng.set_weights(w)
+    parts = eng.train_step(x, y, _lib.PREPROC_MOBILENET)
+    assert abs(parts[0] - loss) <= 5e-3 * max(1.0, abs(loss)), (parts, loss)
+    for i, (g, r) in enumerate(zip(eng.get_grads(), ref_grads)):
+        assert np.linalg.norm((g - r).ravel()) <= 1e-6 + 3e-2 * np.linalg.norm(r.ravel()), i
+
+
 @pytest.mark.parametrize("n_classes,shape", [(0, (2, 64, 96)), (4, (3, 48, 80)), (0, (2, 128, 640)), (0, (1, 80, 1040))])
 def test_tensor_core_training_step_matches_oracle(n_classes, shape):
     """The tf32 handle's training step against the autograd oracle (float32 torch-CPU) and against the library's exact
