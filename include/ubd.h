@@ -177,6 +177,11 @@ int ubd_grad_buffer(ubd_handle h, void** d_ptr, int64_t* n_floats);
 /* Keras-2 Adam (train.py:110): grads are multiplied by grad_scale first (1/world after a sum
  * all-reduce); step count is kept in the handle. */
 int ubd_adam_step(ubd_handle h, float lr, float beta_1, float beta_2, float epsilon, float grad_scale);
+/* One whole optimizer step with a single host synchronisation (Keras train_on_batch as train.py:110-112 drives it):
+ * ubd_train_step + ubd_allreduce_grads (when ubd_comm_init has been called; Adam then scales by 1 / world) +
+ * ubd_adam_step, queued back to back; loss_parts as ubd_train_step. */
+int ubd_train_update(ubd_handle h, const void* images, int in_dtype, int n, int height, int width, int preproc,
+                     const int32_t* y_true, float lr, float beta_1, float beta_2, float epsilon, float* loss_parts);
 
 /* Data-parallel training exchange (one process per GPU; the reference is single-GPU, train.py): rank 0 creates a
  * 128-byte NCCL unique id and hands it to every rank out of band; each rank joins with ubd_comm_init; between

@@ -289,3 +289,22 @@ def test_tensor_core_training_full_size_reproducible_and_learns():
         eng.adam_step(lr=2e-3)
         losses.append(eng.train_step(x, y, _lib.PREPROC_MOBILENET)[0])
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_train_update_equals_step_plus_adam(precision):
+    """ubd_train_update (step, exchange, Adam queued back to back, one host synchronisation) leaves exactly the weights,
+    loss parts and Adam state that ubd_train_step + ubd_adam_step leave, over three consecutive steps."""
+    w = onet.init_weights(2, seed=4)
+    x = synth.synth_images(2, 64, 96, seed=5)
+    y = synth.synth_targets(2, 16, 24, 2, seed=5)
+    a = _engine(n_classes=2, precision=precision); a.set_weights(w)
+    b = _engine(n_classes=2, precision=precision); b.set_weights(w)
+    for _ in range(3):
+        pa = a.train_step(x, y, _lib.PREPROC_MOBILENET)
+        a.adam_step(lr=2e-3)
+        pb = b.train_update(x, y, _lib.PREPROC_MOBILENET, lr=2e-3)
+        assert np.array_equal(pa, pb)
+    for u, v in zip(a.get_weights(), b.get_weights()):
+        assert np.array_equal(u, v)
+    assert any(not np.array_equal(u, v) for u, v in zip(w, b.get_weights()))

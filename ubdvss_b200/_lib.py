@@ -63,6 +63,7 @@ SIGNATURES = {
     "ubd_get_grads": (_i, [_vp, _pp, _pi64, _i]),
     "ubd_grad_buffer": (_i, [_vp, _pp, _pi64]),
     "ubd_adam_step": (_i, [_vp, _f, _f, _f, _f, _f]),
+    "ubd_train_update": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _f, _vp]),
     "ubd_metric_counts": (_i, [_vp, _vp]),
     "ubd_comm_unique_id": (_i, [_vp]),
     "ubd_comm_init": (_i, [_vp, _vp, _i, _i]),

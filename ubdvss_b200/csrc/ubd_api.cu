@@ -173,6 +173,7 @@ extern "C" int ubd_destroy(ubd_handle h) {
     if (R.ev_fwd) cudaEventDestroy(R.ev_fwd);
   }
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->h_parts) cudaFreeHost(h->h_parts);
   if (h->rec_stream) cudaStreamDestroy(h->rec_stream);
   if (h->cc_stream) cudaStreamDestroy(h->cc_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);

@@ -105,6 +105,7 @@ struct ubd_handle_s {
   const int* last_ytrue = nullptr;
   size_t loss_pixels = 0;         // pixels of the logits / targets of the last loss evaluation (ubd_metric_counts)
   void* h_stage = nullptr;        // pinned staging (unused unless requested)
+  float* h_parts = nullptr;       // pinned loss parts of a deferred training step (ubd_train_update)
 
   std::vector<DevBuf*> all_bufs() {
     std::vector<DevBuf*> v = {&d_images, &d_logits, &d_mask, &act1, &act2, &mapA, &mapB, &mapC, &outer, &parent, &labels, &slot_of, &comps,

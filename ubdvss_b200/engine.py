@@ -166,6 +166,15 @@ class Engine:
         check(self._h, self._lib.ubd_train_step(self._h, ptr(x), dt, n, H, W, preproc, ptr(y), ptr(parts)))
         return parts
 
+    def train_update(self, images, y_true, preproc: int = _lib.PREPROC_NONE, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        """train_step + gradient all-reduce (if ``comm_init`` was called) + Adam with one host synchronisation."""
+        x, dt = self._images(images)
+        n, H, W, _ = x.shape
+        y = np.ascontiguousarray(np.asarray(y_true).reshape(n, H // 4, W // 4), dtype=np.int32)
+        parts = np.zeros(6, np.float32)
+        check(self._h, self._lib.ubd_train_update(self._h, ptr(x), dt, n, H, W, preproc, ptr(y), lr, beta_1, beta_2, epsilon, ptr(parts)))
+        return parts
+
     def loss(self, logits, y_true):
         lg = np.ascontiguousarray(logits, dtype=np.float32)
         n, mh, mw, c = lg.shape
@@ -196,6 +205,10 @@ class Engine:
         assert buf.size == 128
         check(self._h, self._lib.ubd_comm_init(self._h, ptr(buf), int(rank), int(world)))
         self.world = int(world)
+
+    def comm_destroy(self):
+        check(self._h, self._lib.ubd_comm_destroy(self._h))
+        self.world = 1
 
     def allreduce_grads(self):
         """Sum of the flat gradient buffer over the ranks, in place, on the handle's stream."""

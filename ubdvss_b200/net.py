@@ -336,6 +336,8 @@ class B200Model:
         (``ubd_comm_init`` / ``ubd_allreduce_grads``); ``torch.distributed`` only carries the 128-byte unique id.
         ``native=False``: all-reduce through ``torch.distributed`` on the raw device buffer."""
         if not enabled:
+            if getattr(self, "_native_comm", False):
+                self._engine.comm_destroy()          # train_update would otherwise keep exchanging gradients
             self._dist = None
             self._native_comm = False
             return
@@ -371,9 +373,13 @@ class B200Model:
         """One optimizer step; returns ``[loss, positive, negative, hard_negative(, classification)]``."""
         if self._optimizer is None:
             raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
-        parts = self._engine.train_step(x, y, _PREPROC_CODE[preprocessing])
-        scale = self._allreduce_grads() if self._dist is not None else 1.0
         o = self._optimizer
+        if self._dist is None or getattr(self, "_native_comm", False):
+            # step, gradient exchange inside the library and Adam queued back to back: one host synchronisation
+            parts = self._engine.train_update(x, y, _PREPROC_CODE[preprocessing], o.lr, o.beta_1, o.beta_2, o.epsilon)
+            return self._batch_outputs(parts)
+        parts = self._engine.train_step(x, y, _PREPROC_CODE[preprocessing])
+        scale = self._allreduce_grads()
         self._engine.adam_step(o.lr, o.beta_1, o.beta_2, o.epsilon, scale)
         return self._batch_outputs(parts)
 
