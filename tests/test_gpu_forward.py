@@ -274,3 +274,24 @@ def test_f16_containers_track_tf32():
     eng = _engine(precision="f16")
     eng.set_weights(big)
     assert np.isfinite(eng.forward(x[:1], _lib.PREPROC_MOBILENET)).all()
+
+
+@pytest.mark.parametrize("n_classes,fml,grey", [(0, True, True), (5, False, True), (26, True, True), (2, True, False)])
+def test_random_shape_sweep(n_classes, fml, grey):
+    """Random ragged shapes (strip remainders of 8 / 16 px at half resolution, maps narrower than a warp, very wide and
+    very tall maps) through every tensor-core precision: forward against the oracle, and ubd_segment's logits / mask against
+    the forward (fused head + threshold, class-head write-out through shared memory)."""
+    rng = np.random.default_rng(7 + n_classes)
+    shapes = [(16 * int(rng.integers(1, 12)), 16 * int(rng.integers(1, 70))) for _ in range(5)] + \
+             [(32, 528), (48, 1040), (16, 1056), (16, 4112), (208, 16)]
+    w = onet.init_weights(n_classes, seed=11, grey=grey)
+    for precision in ("tf32", "f16", "bf16"):
+        eng = _engine(grey=grey, fml_compatible=fml, n_classes=n_classes, precision=precision)
+        eng.set_weights(w)
+        for (H, W) in shapes:
+            n = int(rng.integers(1, 4))
+            x = synth.synth_images(n, H, W, seed=H + W, channels=1 if grey else 3)
+            got, _ = _check(eng, w, x, _lib.PREPROC_MOBILENET, fml=fml, precision=precision)
+            mask, logits, _, _, _ = eng.segment(x, 0.0, 10, _lib.PREPROC_MOBILENET)
+            assert np.array_equal(logits, got), (precision, H, W)
+            assert np.array_equal(mask, (got[..., 0] > 0).astype(np.uint8))
