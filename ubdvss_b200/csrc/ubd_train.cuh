@@ -358,6 +358,44 @@ xty_kernel(XL xl, YL yl, PixelGeom g, int KY, float* __restrict__ partials /*[gr
   if ((int)threadIdx.x < KY) o[nout + threadIdx.x] = colsum;
 }
 
+// Weight + bias gradient of a one-output head (detection only: net.py:307-311 with C = 0): dHK[c] = sum_px a[px][c] *
+// dl[px], dHB = sum_px dl[px].  One pass over the last map; per-block partial sums in a fixed order.
+__global__ void __launch_bounds__(256)
+head_wgrad1_kernel(const float4* __restrict__ a, const float* __restrict__ dl, int N, int H, int W, int mpad,
+                   float* __restrict__ partials /*[grid][25]*/) {
+  __shared__ float red[8][UBD_NF + 1];
+  float acc[UBD_NF + 1];
+#pragma unroll
+  for (int c = 0; c <= UBD_NF; ++c) acc[c] = 0.f;
+  const size_t P = (size_t)N * H * W;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((size_t)W * H));
+    const float d = __ldg(&dl[p]);
+#pragma unroll
+    for (int g = 0; g < UBD_NG; ++g) {
+      const float4 v = __ldg(&a[act_index(n, g, y, x, H, W, mpad)]);
+      acc[4 * g] = fmaf(v.x, d, acc[4 * g]); acc[4 * g + 1] = fmaf(v.y, d, acc[4 * g + 1]);
+      acc[4 * g + 2] = fmaf(v.z, d, acc[4 * g + 2]); acc[4 * g + 3] = fmaf(v.w, d, acc[4 * g + 3]);
+    }
+    acc[UBD_NF] += d;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c <= UBD_NF; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[wid][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= UBD_NF) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    partials[(size_t)blockIdx.x * (UBD_NF + 1) + threadIdx.x] = v;
+  }
+}
+
 // out[i] = sum_b partials[b][i] in a fixed order (deterministic); two destinations (kernel, bias).  Eight lanes share an
 // output: lane l adds the blocks b = l, l + 8, ... in order, then the eight sums are combined as a fixed tree.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nblocks, int stride,
@@ -502,35 +540,44 @@ dw_bwd_weight_kernel(const float4* __restrict__ xin, const float4* __restrict__ 
 }
 
 // g_x[q][c] = (x[q][c] > 0) * sum_taps g_d[(q + pad - tap) / s][c] * dw[tap][c]   (transposed depthwise)
+// Block = 32 pixels x 6 planes, DW_ROWS rows per block: the thread's 9 x 4 weights are loaded once, the stride is a
+// template parameter (the run-time % and / per tap dominated the first version: 225 us per half-resolution map).
+constexpr int DW_ROWS = 8;
+template <int STRIDE>
 __global__ void __launch_bounds__(192)
 dw_bwd_data_kernel(const float4* __restrict__ gd, const float4* __restrict__ xin, float4* __restrict__ gx,
                    const float* __restrict__ dwk, int N, int Hi, int Wi, int ipad, int Ho, int Wo, int opad,
-                   int stride, int pad_t, int pad_l) {
+                   int pad_t, int pad_l) {
   const int pl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y, n = blockIdx.z;
+  const int x = blockIdx.x * 32 + lane, n = blockIdx.z;
   if (x >= Wi) return;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 wk[9];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int yy = y + pad_t - i;
-    if (yy < 0 || yy % stride) continue;
-    const int oy = yy / stride;
-    if (oy >= Ho) continue;
+  for (int t = 0; t < 9; ++t) wk[t] = __ldg(reinterpret_cast<const float4*>(dwk + t * UBD_NF + 4 * pl));
+  const int y0 = blockIdx.y * DW_ROWS;
+  for (int y = y0; y < min(y0 + DW_ROWS, Hi); ++y) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int xx = x + pad_l - j;
-      if (xx < 0 || xx % stride) continue;
-      const int ox = xx / stride;
-      if (ox >= Wo) continue;
-      const float4 g = __ldg(&gd[act_index(n, pl, oy, ox, Ho, Wo, opad)]);
-      const float* wk = dwk + (i * 3 + j) * UBD_NF + 4 * pl;
-      s.x = fmaf(g.x, __ldg(wk), s.x); s.y = fmaf(g.y, __ldg(wk + 1), s.y);
-      s.z = fmaf(g.z, __ldg(wk + 2), s.z); s.w = fmaf(g.w, __ldg(wk + 3), s.w);
+    for (int i = 0; i < 3; ++i) {
+      const int yy = y + pad_t - i;
+      if (yy < 0 || (yy % STRIDE)) continue;
+      const int oy = yy / STRIDE;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int xx = x + pad_l - j;
+        if (xx < 0 || (xx % STRIDE)) continue;
+        const int ox = xx / STRIDE;
+        if (ox >= Wo) continue;
+        const float4 g = __ldg(&gd[act_index(n, pl, oy, ox, Ho, Wo, opad)]);
+        const float4 w4 = wk[i * 3 + j];
+        s.x = fmaf(g.x, w4.x, s.x); s.y = fmaf(g.y, w4.y, s.y); s.z = fmaf(g.z, w4.z, s.z); s.w = fmaf(g.w, w4.w, s.w);
+      }
     }
+    const size_t idx = act_index(n, pl, y, x, Hi, Wi, ipad);
+    const float4 a = __ldg(&xin[idx]);
+    gx[idx] = make_float4(a.x > 0.f ? s.x : 0.f, a.y > 0.f ? s.y : 0.f, a.z > 0.f ? s.z : 0.f, a.w > 0.f ? s.w : 0.f);
   }
-  const size_t idx = act_index(n, pl, y, x, Hi, Wi, ipad);
-  const float4 a = __ldg(&xin[idx]);
-  gx[idx] = make_float4(a.x > 0.f ? s.x : 0.f, a.y > 0.f ? s.y : 0.f, a.z > 0.f ? s.z : 0.f, a.w > 0.f ? s.w : 0.f);
 }
 
 // First layer (raw image input, CIN = 1 or 3): all three weight gradients in one pass.
